@@ -1,0 +1,128 @@
+// BLS12-381 field layer for sm_100a: thin value-semantic wrappers over the generated
+// inline-PTX routines in field_ptx.cuh, plus Fq2 = Fq[u]/(u^2+1).
+//
+// Replaces (behaviourally) the reference's Field<Config> free functions
+//   field_add/sub/neg/mul/sqr/inv/to_montgomery/from_montgomery
+//   bls12-381/include/field.cuh:389-928  and  fq2_* bls12-381/include/point.cuh:131-225.
+// Contract kept from the reference: little-endian u64 limbs, Montgomery domain with
+// R = 2^384 (Fq) / 2^256 (Fr), every result canonical (< modulus), inv(0) = 0.
+#pragma once
+#ifdef B381_HOST_TEST
+// CPU-only unit-test build of the per-thread device code (tests/host/); never shipped.
+#include "field_host_shim.h"
+#include "field_consts.h"
+#define B381_DI inline
+#else
+#include "field_ptx.cuh"
+#define B381_DI __device__ __forceinline__
+#endif
+
+namespace b381 {
+
+// ------------------------------------------------------------------ constants
+B381_DI fq_t fq_modulus() { return fq_t{FQ_MODULUS_INIT}; }
+B381_DI fr_t fr_modulus() { return fr_t{FR_MODULUS_INIT}; }
+
+template <class F> B381_DI F zero();
+template <class F> B381_DI F one();
+template <> B381_DI fq_t zero<fq_t>() { return fq_t{{0, 0, 0, 0, 0, 0}}; }
+template <> B381_DI fr_t zero<fr_t>() { return fr_t{{0, 0, 0, 0}}; }
+template <> B381_DI fq_t one<fq_t>() { return fq_t{FQ_ONE_INIT}; }
+template <> B381_DI fr_t one<fr_t>() { return fr_t{FR_ONE_INIT}; }
+
+// ------------------------------------------------------------------ Fq / Fr
+B381_DI fq_t mul(const fq_t& a, const fq_t& b) { fq_t r; fq_mul_raw(r, a, b); return r; }
+B381_DI fq_t sqr(const fq_t& a) { fq_t r; fq_sqr_raw(r, a); return r; }
+B381_DI fq_t add(const fq_t& a, const fq_t& b) { fq_t r; fq_add_raw(r, a, b); return r; }
+B381_DI fq_t sub(const fq_t& a, const fq_t& b) { fq_t r; fq_sub_raw(r, a, b); return r; }
+B381_DI fq_t neg(const fq_t& a) { fq_t r; fq_neg_raw(r, a); return r; }
+B381_DI fq_t dbl(const fq_t& a) { fq_t r; fq_dbl_raw(r, a); return r; }
+
+B381_DI fr_t mul(const fr_t& a, const fr_t& b) { fr_t r; fr_mul_raw(r, a, b); return r; }
+B381_DI fr_t sqr(const fr_t& a) { fr_t r; fr_sqr_raw(r, a); return r; }
+B381_DI fr_t add(const fr_t& a, const fr_t& b) { fr_t r; fr_add_raw(r, a, b); return r; }
+B381_DI fr_t sub(const fr_t& a, const fr_t& b) { fr_t r; fr_sub_raw(r, a, b); return r; }
+B381_DI fr_t neg(const fr_t& a) { fr_t r; fr_neg_raw(r, a); return r; }
+B381_DI fr_t dbl(const fr_t& a) { fr_t r; fr_dbl_raw(r, a); return r; }
+
+B381_DI bool is_zero(const fq_t& a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3] | a.l[4] | a.l[5]) == 0; }
+B381_DI bool is_zero(const fr_t& a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
+B381_DI bool eq(const fq_t& a, const fq_t& b) {
+  return ((a.l[0] ^ b.l[0]) | (a.l[1] ^ b.l[1]) | (a.l[2] ^ b.l[2]) | (a.l[3] ^ b.l[3]) |
+          (a.l[4] ^ b.l[4]) | (a.l[5] ^ b.l[5])) == 0;
+}
+B381_DI bool eq(const fr_t& a, const fr_t& b) {
+  return ((a.l[0] ^ b.l[0]) | (a.l[1] ^ b.l[1]) | (a.l[2] ^ b.l[2]) | (a.l[3] ^ b.l[3])) == 0;
+}
+
+// Montgomery <-> standard (reference: field.cuh:906-928)
+B381_DI fq_t to_mont(const fq_t& a) { return mul(a, fq_t{FQ_R2_INIT}); }
+B381_DI fr_t to_mont(const fr_t& a) { return mul(a, fr_t{FR_R2_INIT}); }
+B381_DI fq_t from_mont(const fq_t& a) { fq_t o = {{1, 0, 0, 0, 0, 0}}; return mul(a, o); }
+B381_DI fr_t from_mont(const fr_t& a) { fr_t o = {{1, 0, 0, 0}}; return mul(a, o); }
+
+// a^(m-2) by plain square-and-multiply; only ever runs on single-thread tails
+// (one inversion per MSM, n^-1 per NTT domain).  inv(0) = 0 as in field.cuh:750-900.
+template <class F, int N64>
+B381_DI F pow_m_minus_2(const F& a, const uint64_t (&m)[N64]) {
+  uint64_t e[N64];
+#pragma unroll
+  for (int i = 0; i < N64; i++) e[i] = m[i];
+  e[0] -= 2;  // both moduli end in ...01 / ...ab, no borrow
+  F r = one<F>();
+#pragma unroll 1
+  for (int i = N64 * 64 - 1; i >= 0; i--) {
+    r = sqr(r);
+    if ((e[i >> 6] >> (i & 63)) & 1) r = mul(r, a);
+  }
+  return r;
+}
+B381_DI fq_t inv(const fq_t& a) { const uint64_t m[6] = FQ_MODULUS_INIT; return pow_m_minus_2<fq_t, 6>(a, m); }
+B381_DI fr_t inv(const fr_t& a) { const uint64_t m[4] = FR_MODULUS_INIT; return pow_m_minus_2<fr_t, 4>(a, m); }
+
+// r = a^e for a 64-bit exponent (twiddle / coset power setup)
+template <class F>
+B381_DI F pow_u64(const F& a, uint64_t e) {
+  F r = one<F>();
+  F b = a;
+#pragma unroll 1
+  while (e) {
+    if (e & 1) r = mul(r, b);
+    b = sqr(b);
+    e >>= 1;
+  }
+  return r;
+}
+
+// ------------------------------------------------------------------ Fq2
+struct fq2_t { fq_t c0, c1; };
+template <> B381_DI fq2_t zero<fq2_t>() { return fq2_t{zero<fq_t>(), zero<fq_t>()}; }
+template <> B381_DI fq2_t one<fq2_t>() { return fq2_t{one<fq_t>(), zero<fq_t>()}; }
+
+B381_DI fq2_t add(const fq2_t& a, const fq2_t& b) { return fq2_t{add(a.c0, b.c0), add(a.c1, b.c1)}; }
+B381_DI fq2_t sub(const fq2_t& a, const fq2_t& b) { return fq2_t{sub(a.c0, b.c0), sub(a.c1, b.c1)}; }
+B381_DI fq2_t neg(const fq2_t& a) { return fq2_t{neg(a.c0), neg(a.c1)}; }
+B381_DI fq2_t dbl(const fq2_t& a) { return fq2_t{dbl(a.c0), dbl(a.c1)}; }
+B381_DI fq2_t mul(const fq2_t& a, const fq2_t& b) {
+  // Karatsuba, 3 Fq products
+  fq_t v0 = mul(a.c0, b.c0);
+  fq_t v1 = mul(a.c1, b.c1);
+  fq_t s = mul(add(a.c0, a.c1), add(b.c0, b.c1));
+  return fq2_t{sub(v0, v1), sub(sub(s, v0), v1)};
+}
+B381_DI fq2_t sqr(const fq2_t& a) {
+  // (a0+a1)(a0-a1) + 2 a0 a1 u, 2 Fq products
+  fq_t t = mul(a.c0, a.c1);
+  fq_t c0 = mul(add(a.c0, a.c1), sub(a.c0, a.c1));
+  return fq2_t{c0, dbl(t)};
+}
+B381_DI bool is_zero(const fq2_t& a) { return is_zero(a.c0) && is_zero(a.c1); }
+B381_DI bool eq(const fq2_t& a, const fq2_t& b) { return eq(a.c0, b.c0) && eq(a.c1, b.c1); }
+B381_DI fq2_t inv(const fq2_t& a) {
+  fq_t n = inv(add(sqr(a.c0), sqr(a.c1)));
+  return fq2_t{mul(a.c0, n), neg(mul(a.c1, n))};
+}
+B381_DI fq2_t to_mont(const fq2_t& a) { return fq2_t{to_mont(a.c0), to_mont(a.c1)}; }
+B381_DI fq2_t from_mont(const fq2_t& a) { return fq2_t{from_mont(a.c0), from_mont(a.c1)}; }
+
+}  // namespace b381

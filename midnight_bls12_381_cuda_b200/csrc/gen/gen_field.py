@@ -1,0 +1,305 @@
+#!/usr/bin/env python3
+"""Generate `field_ptx.cuh`: Montgomery arithmetic for BLS12-381 Fq (12x32-bit
+limbs) and Fr (8x32-bit limbs) as single inline-PTX blocks for sm_100a.
+
+Design (our own; the reference uses `unsigned __int128` C++ in
+bls12-381/include/field.cuh:510-685 and has no inline asm at all):
+
+  * 32-bit limbs.  Every 32x32->64 product is written as a `mad.lo.cc` /
+    `madc.hi.cc` pair on an adjacent register pair so that ptxas emits ONE
+    `IMAD.WIDE.U32(.X)` per product (verified with cuobjdump).
+  * Operand-scanning Montgomery (CIOS flavour) with TWO accumulators:
+    `E` collects the products that start on an even limb, `O` those that start
+    on an odd limb, so both carry chains run over aligned (lo,hi) pairs and no
+    chain needs a 32-bit realignment.  After each word of b the total
+    T = E + O*2^32 is divisible by 2^32; the division renames E<->O.
+  * Modulus limbs and -m^-1 mod 2^32 are immediates (no constant-bank loads,
+    no registers held across the routine).
+  * Outputs are always canonical (< m), like the reference's field_mul.
+
+Each routine is built as a `ptxir.Block`, *executed in Python against big
+integers* (tests/test_gen_field.py), and only then printed as PTX.
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+from ptxir import Block, M32  # noqa: E402
+
+BLS_X = -0xD201000000010000
+R_MOD = BLS_X**4 - BLS_X**2 + 1
+P_MOD = ((BLS_X - 1) ** 2 * R_MOD) // 3 + BLS_X
+
+
+def limbs32(v: int, n: int) -> list[int]:
+    return [(v >> (32 * i)) & M32 for i in range(n)]
+
+
+class FieldSpec:
+    def __init__(self, name: str, modulus: int, n32: int):
+        self.name = name
+        self.m = modulus
+        self.n = n32
+        self.p = limbs32(modulus, n32)
+        self.m0 = (-pow(modulus, -1, 1 << 32)) % (1 << 32)
+        self.R = (1 << (32 * n32)) % modulus
+        self.R2 = self.R * self.R % modulus
+
+
+FQ = FieldSpec("fq", P_MOD, 12)
+FR = FieldSpec("fr", R_MOD, 8)
+
+
+# ---------------------------------------------------------------------------
+# building blocks
+# ---------------------------------------------------------------------------
+def final_sub(b: Block, f: FieldSpec, r: list, outs: list[str], top=None):
+    """outs = r - m if r >= m else r   (r < 2m; `top` = optional extra high limb)."""
+    n = f.n
+    t = []
+    for k in range(n):
+        op = "sub.cc.u32" if k == 0 else "subc.cc.u32"
+        t.append(b.op3(op, r[k], f.p[k]))
+    if top is None:
+        mask = b.op3("subc.u32", 0, 0)        # 0xffffffff if borrow (r < m) else 0
+    else:
+        mask = b.op3("subc.u32", top, 0)      # borrow only if top==0 and chain borrowed
+    for k in range(n):
+        b.mask_select(mask, r[k], t[k], dst=outs[k])
+
+
+def reduce_step(b: Block, f: FieldSpec, E: list, O: list):
+    """E,O += m_i * modulus so that E[0] becomes 0; carries folded into O[n-1]."""
+    n = f.n
+    mi = b.op3("mul.lo.u32", E[0], f.m0)
+    # odd limbs of the modulus -> O pairs
+    for j in range(1, n, 2):
+        lo = "mad.lo.cc.u32" if j == 1 else "madc.lo.cc.u32"
+        O[j - 1] = b.op4(lo, mi, f.p[j], O[j - 1])
+        hi = "madc.hi.cc.u32" if j < n - 1 else "madc.hi.u32"
+        O[j] = b.op4(hi, mi, f.p[j], O[j])
+    # even limbs of the modulus -> E pairs
+    for j in range(0, n, 2):
+        lo = "mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32"
+        E[j] = b.op4(lo, mi, f.p[j], E[j])
+        E[j + 1] = b.op4("madc.hi.cc.u32", mi, f.p[j], E[j + 1])
+    O[n - 1] = b.op3("addc.u32", O[n - 1], 0)
+
+
+def mont_mul_body(b: Block, f: FieldSpec, a: list, bb: list, outs: list[str]):
+    n = f.n
+    E = [None] * n
+    O = [None] * n
+    # ---- word 0 of b: plain products
+    for j in range(0, n, 2):
+        E[j] = b.op3("mul.lo.u32", a[j], bb[0])
+        E[j + 1] = b.op3("mul.hi.u32", a[j], bb[0])
+    for j in range(1, n, 2):
+        O[j - 1] = b.op3("mul.lo.u32", a[j], bb[0])
+        O[j] = b.op3("mul.hi.u32", a[j], bb[0])
+    reduce_step(b, f, E, O)
+    # ---- words 1..n-1
+    for i in range(1, n):
+        Eo, Oo = E, O
+        E = list(Oo)                 # old O is now aligned on limb 0
+        O = [None] * n
+        E[0] = b.op3("add.cc.u32", E[0], Eo[1])
+        for j in range(1, n, 2):
+            if j < n - 1:
+                O[j - 1] = b.op4("madc.lo.cc.u32", a[j], bb[i], Eo[j + 1])
+                O[j] = b.op4("madc.hi.cc.u32", a[j], bb[i], Eo[j + 2])
+            else:
+                O[j - 1] = b.op4("madc.lo.cc.u32", a[j], bb[i], 0)
+                O[j] = b.op4("madc.hi.u32", a[j], bb[i], 0)
+        for j in range(0, n, 2):
+            lo = "mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32"
+            E[j] = b.op4(lo, a[j], bb[i], E[j])
+            E[j + 1] = b.op4("madc.hi.cc.u32", a[j], bb[i], E[j + 1])
+        O[n - 1] = b.op3("addc.u32", O[n - 1], 0)
+        reduce_step(b, f, E, O)
+    # ---- merge: result[k] = O[k] + E[k+1]
+    r = [None] * n
+    r[0] = b.op3("add.cc.u32", O[0], E[1])
+    for k in range(1, n - 1):
+        r[k] = b.op3("addc.cc.u32", O[k], E[k + 1])
+    r[n - 1] = b.op3("addc.u32", O[n - 1], 0)
+    final_sub(b, f, r, outs)
+
+
+def add_body(b: Block, f: FieldSpec, a, bb, outs):
+    n = f.n
+    s = []
+    for k in range(n):
+        op = "add.cc.u32" if k == 0 else ("addc.cc.u32" if k < n - 1 else "addc.u32")
+        s.append(b.op3(op, a[k], bb[k]))
+    final_sub(b, f, s, outs)     # both moduli leave >= 1 spare bit, so a+b < 2^(32n)
+
+
+def sub_body(b: Block, f: FieldSpec, a, bb, outs):
+    n = f.n
+    d = []
+    for k in range(n):
+        op = "sub.cc.u32" if k == 0 else "subc.cc.u32"
+        d.append(b.op3(op, a[k], bb[k]))
+    mask = b.op3("subc.u32", 0, 0)            # all-ones if a < b
+    for k in range(n):
+        pk = b.op3("and.b32", mask, f.p[k])
+        op = "add.cc.u32" if k == 0 else ("addc.cc.u32" if k < n - 1 else "addc.u32")
+        b.op3(op, d[k], pk, dst=outs[k])
+
+
+def neg_body(b: Block, f: FieldSpec, a, outs):
+    """-a mod m, with -0 = 0."""
+    n = f.n
+    nz = a[0]
+    for k in range(1, n):
+        nz = b.op3("or.b32", nz, a[k])
+    d = []
+    for k in range(n):
+        op = "sub.cc.u32" if k == 0 else ("subc.cc.u32" if k < n - 1 else "subc.u32")
+        d.append(b.op3(op, f.p[k], a[k]))
+    for k in range(n):
+        b.mask_select(nz, d[k], 0, dst=outs[k])
+
+
+# ---------------------------------------------------------------------------
+# routine table
+# ---------------------------------------------------------------------------
+def build(f: FieldSpec, op: str) -> Block:
+    n = f.n
+    b = Block(f"{f.name}_{op}")
+    outs = [f"r{k}" for k in range(n)]
+    b.outputs = outs
+    a = [b.inp(f"a{k}") for k in range(n)]
+    if op in ("mul", "add", "sub"):
+        bb = [b.inp(f"b{k}") for k in range(n)]
+    if op == "mul":
+        mont_mul_body(b, f, a, bb, outs)
+    elif op == "sqr":
+        mont_mul_body(b, f, a, a, outs)
+    elif op == "add":
+        add_body(b, f, a, bb, outs)
+    elif op == "sub":
+        sub_body(b, f, a, bb, outs)
+    elif op == "neg":
+        neg_body(b, f, a, outs)
+    elif op == "dbl":
+        add_body(b, f, a, a, outs)
+    else:
+        raise ValueError(op)
+    return b
+
+
+OPS = ["mul", "sqr", "add", "sub", "neg", "dbl"]
+
+
+def run_block(blk: Block, f: FieldSpec, *vals: int) -> int:
+    env = {}
+    names = ["a", "b"]
+    for nm, v in zip(names, vals):
+        for k, l in enumerate(limbs32(v, f.n)):
+            env[f"{nm}{k}"] = l
+    r = blk.run(env)
+    return sum(r[f"r{k}"] << (32 * k) for k in range(f.n))
+
+
+# ---------------------------------------------------------------------------
+# C++ emission
+# ---------------------------------------------------------------------------
+def emit_cpp(blk: Block, f: FieldSpec, nin: int) -> str:
+    n = f.n
+    n64 = n // 2
+    lines = blk.ptx_lines()
+    decl = [f".reg .u32 t<{max(blk.nreg, 1)}>;",
+            f".reg .u32 a<{n}>, b<{n}>, r<{n}>;"]
+    if getattr(blk, "_npredsel", 0):
+        decl.append(f".reg .pred q<{blk._npredsel}>;")
+    body = ["{"] + decl
+    # operand numbering: outputs 0..n64-1, then a, then b
+    for k in range(n64):
+        body.append(f"mov.b64 {{a{2*k}, a{2*k+1}}}, %{n64 + k};")
+    if nin == 2:
+        for k in range(n64):
+            body.append(f"mov.b64 {{b{2*k}, b{2*k+1}}}, %{2 * n64 + k};")
+    body += lines
+    for k in range(n64):
+        body.append(f"mov.b64 %{k}, {{r{2*k}, r{2*k+1}}};")
+    body.append("}")
+    text = "\n".join(f'      "{l}\\n\\t"' for l in body)
+    T = f"{f.name}_t"
+    args = f"{T}& r, const {T}& a" + (f", const {T}& b" if nin == 2 else "")
+    outs = ", ".join(f'"=l"(r.l[{k}])' for k in range(n64))
+    ins = ", ".join(f'"l"(a.l[{k}])' for k in range(n64))
+    if nin == 2:
+        ins += ", " + ", ".join(f'"l"(b.l[{k}])' for k in range(n64))
+    # NB: outputs are written only at the very end of the block, after every input has been
+    # read into a/b registers, so plain "=l" (no early-clobber) is safe even when r aliases a or b.
+    return (f"__device__ __forceinline__ void {blk.name}_raw({args}) {{\n"
+            f"  asm(\n{text}\n      : {outs}\n      : {ins});\n}}\n")
+
+
+HEADER = """// GENERATED by csrc/gen/gen_field.py -- do not edit.
+// Montgomery arithmetic for BLS12-381 Fq (6x64 = 12x32 limbs) and Fr (4x64 = 8x32 limbs),
+// one inline-PTX block per routine (carry flag never leaves a block).
+// Replaces the reference's C++ `unsigned __int128` field_mul/field_sqr/field_add/field_sub
+// (bls12-381/include/field.cuh:389-685) on the hot path.
+#pragma once
+#include <cstdint>
+#include "field_consts.h"
+
+struct fq_t { uint64_t l[6]; };
+struct fr_t { uint64_t l[4]; };
+
+"""
+
+
+def _c64(v: int, n64: int) -> str:
+    return "{" + ", ".join(f"0x{(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF:016x}ull" for i in range(n64)) + "}"
+
+
+def constants() -> str:
+    """Curve constants, all derived from the BLS parameter x (see oracle/pyref.py, which derives
+    the same values independently and checks them against the spec literals)."""
+    out = []
+    for f in (FQ, FR):
+        N = f.name.upper()
+        n64 = f.n // 2
+        out.append(f"#define {N}_LIMBS {n64}")
+        out.append(f"#define {N}_MODULUS_INIT {_c64(f.m, n64)}")
+        out.append(f"#define {N}_ONE_INIT {_c64(f.R, n64)}        /* R mod m */")
+        out.append(f"#define {N}_R2_INIT {_c64(f.R2, n64)}         /* R^2 mod m */")
+        out.append(f"#define {N}_INV32 0x{f.m0:08x}u          /* -m^-1 mod 2^32 */")
+    g1x = 0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB
+    g1y = 0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1
+    out.append(f"#define G1_GEN_X_MONT_INIT {_c64(g1x * FQ.R % FQ.m, 6)}")
+    out.append(f"#define G1_GEN_Y_MONT_INIT {_c64(g1y * FQ.R % FQ.m, 6)}")
+    # Fr: 2^32-th root of unity 7^((r-1)/2^32), Montgomery form
+    w = pow(7, (FR.m - 1) >> 32, FR.m)
+    out.append(f"#define FR_ROOT_OF_UNITY_MONT_INIT {_c64(w * FR.R % FR.m, 4)}")
+    out.append("")
+    return "\n".join(out) + "\n"
+
+
+def generate() -> str:
+    out = [HEADER]
+    for f in (FQ, FR):
+        for op in OPS:
+            blk = build(f, op)
+            nin = 2 if op in ("mul", "add", "sub") else 1
+            out.append(emit_cpp(blk, f, nin))
+    return "\n".join(out)
+
+
+if __name__ == "__main__":
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "field_ptx.cuh")
+    with open(dst, "w") as fh:
+        fh.write(generate())
+    with open(os.path.join(os.path.dirname(dst), "field_consts.h"), "w") as fh:
+        fh.write("// GENERATED by csrc/gen/gen_field.py -- do not edit.\n"
+                 "// BLS12-381 constants, derived from the BLS parameter x = -0xd201000000010000.\n"
+                 "#pragma once\n" + constants())
+    for f in (FQ, FR):
+        for op in OPS:
+            print(f.name, op, build(f, op).count())

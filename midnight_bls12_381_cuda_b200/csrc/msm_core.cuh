@@ -1,0 +1,222 @@
+// Per-thread bodies of the Pippenger MSM pipeline (G1 and G2), written so that each CUDA
+// kernel in msm.cu is `body(global_thread_id, ...)`.  The same bodies are driven by a serial
+// loop in tests/host/msm_host_sim.cpp (CPU-only CI), which is how the pipeline logic is
+// checked without a GPU.
+//
+// Pipeline (ours; the reference's is bls12-381/src/curve/msm_kernels.cu:603-903):
+//   1 digits      scalar -> W signed c-bit digits -> (key = w*B + |d|-1, val = idx<<1 | sign);
+//                 zero digits get the trash key W*B.       [ref: compute_bucket_indices_kernel :69-143]
+//   2 sort        device radix sort of (key,val) over ceil(log2(W*B+1)) key bits only
+//                                                           [ref sorts all 32 bits, :768-778]
+//   3 offsets     bucket boundaries straight from the sorted keys (no histogram, no atomics)
+//                                                           [ref: histogram + scan, :224-256,:748-758]
+//   4 tasks       every bucket is cut into ceil(size/K) equal tasks so one thread never owns more
+//                 than K insertions, whatever the scalar distribution
+//                                                           [ref: 1 thread or 8/16 threads per bucket]
+//   5 accumulate  one thread per task: XYZZ mixed additions (8M+2S)     <- the hot loop
+//   6 finalize    bucket = sum of its task partials
+//   7 seg-reduce  segments of L buckets: T_s + (s*L)*A_s  (running-sum trick + short double-and-add)
+//                                                           [ref: 1 CTA per window, :376-513]
+//   8 tree        pairwise sums down to one point per window
+//   9 combine     Horner over windows, to-affine, ICICLE standard-form (x,y,1) result
+//                                                           [ref: :529-596 + icicle_curve_api.cu:134-229]
+#pragma once
+#include "curve.cuh"
+
+namespace b381 {
+
+struct msm_shape {
+  uint32_t n;        // points in this MSM
+  uint32_t c;        // window bits
+  uint32_t W;        // number of windows
+  uint32_t B;        // buckets per window = 2^(c-1)
+  uint32_t nbuckets; // W*B  (key W*B is the trash key)
+};
+
+B381_DI uint32_t ceil_div_u32(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- 1 digits
+// Signed-digit recoding with the same digit set as the reference
+// (msm_kernels.cu:96-130): d in [-(2^(c-1)-1), 2^(c-1)], d > 2^(c-1) => d -= 2^c, carry.
+// keys/vals are window-major ([w*n + i]) so stores coalesce.
+B381_DI void msm_digits_body(uint32_t i, const fr_t* scalars, bool scalars_mont, const msm_shape sh,
+                             uint32_t* keys, uint32_t* vals) {
+  if (i >= sh.n) return;
+  fr_t s = scalars[i];
+  if (scalars_mont) s = from_mont(s);
+  const uint32_t mask = (1u << sh.c) - 1u;
+  uint32_t carry = 0;
+  for (uint32_t w = 0; w < sh.W; w++) {
+    uint32_t bit = w * sh.c;
+    uint32_t limb = bit >> 6, off = bit & 63;
+    uint32_t d = 0;
+    if (limb < 4) {
+      uint64_t lo = s.l[limb] >> off;
+      if (off + sh.c > 64 && limb + 1 < 4) lo |= s.l[limb + 1] << (64 - off);
+      d = (uint32_t)lo & mask;
+    }
+    d += carry;
+    carry = 0;
+    uint32_t sign = 0;
+    if (d > sh.B) {          // B = 2^(c-1)
+      d = (1u << sh.c) - d;
+      sign = 1;
+      carry = 1;
+    }
+    uint32_t key = d ? (w * sh.B + d - 1) : sh.nbuckets;
+    keys[(size_t)w * sh.n + i] = key;
+    vals[(size_t)w * sh.n + i] = (i << 1) | sign;
+  }
+  // W*c >= 256 > bit length of any canonical scalar, so the last carry is always 0.
+}
+
+// ---------------------------------------------------------------- 3 offsets
+// sorted keys -> offsets[0..nbuckets]; offsets[b] = first position with key >= b.
+// offsets[nbuckets] = number of non-trash entries.
+B381_DI void msm_offsets_body(size_t j, const uint32_t* sorted_keys, size_t total, uint32_t nbuckets,
+                              uint32_t* offsets) {
+  if (j > total) return;
+  uint32_t prev = (j == 0) ? 0u : sorted_keys[j - 1] + 1u;          // first key not yet started
+  uint32_t cur = (j == total) ? nbuckets + 1u : sorted_keys[j] + 1u; // one past this key
+  if (j == 0) prev = 0;
+  // every bucket id in [prev, cur) starts at position j
+  for (uint32_t b = prev; b < cur && b <= nbuckets; b++) offsets[b] = (uint32_t)j;
+}
+
+// ---------------------------------------------------------------- 4 tasks
+B381_DI void msm_task_count_body(uint32_t b, const uint32_t* offsets, uint32_t nbuckets, uint32_t K,
+                                 uint32_t* counts) {
+  if (b >= nbuckets) return;
+  uint32_t sz = offsets[b + 1] - offsets[b];
+  counts[b] = ceil_div_u32(sz, K);
+}
+
+B381_DI void msm_build_tasks_body(uint32_t b, const uint32_t* offsets, const uint32_t* task_start,
+                                  uint32_t nbuckets, uint32_t K, uint2* tasks) {
+  if (b >= nbuckets) return;
+  uint32_t beg = offsets[b], sz = offsets[b + 1] - beg;
+  uint32_t nt = ceil_div_u32(sz, K);
+  uint32_t t0 = task_start[b];
+  // equal split: first (sz % nt) tasks get one extra element
+  uint32_t base = nt ? sz / nt : 0, rem = nt ? sz % nt : 0, pos = beg;
+  for (uint32_t t = 0; t < nt; t++) {
+    uint32_t len = base + (t < rem ? 1u : 0u);
+    uint2 tk;
+    tk.x = pos;
+    tk.y = pos + len;
+    tasks[t0 + t] = tk;
+    pos += len;
+  }
+}
+
+// ---------------------------------------------------------------- 5 accumulate (hot)
+template <class F>
+B381_DI void msm_accumulate_body(uint32_t t, uint32_t ntasks, const uint2* tasks, const uint32_t* sorted_vals,
+                                 const affine_t<F>* bases, xyzz_t<F>* partial) {
+  if (t >= ntasks) return;
+  uint2 tk = tasks[t];
+  xyzz_t<F> acc = xyzz_identity<F>();
+  for (uint32_t j = tk.x; j < tk.y; j++) {
+    uint32_t v = sorted_vals[j];
+    affine_t<F> p = bases[v >> 1];
+    if (is_inf(p)) continue;            // (0,0) bases are legal and contribute nothing
+    if (v & 1) p.y = neg(p.y);
+    xyzz_madd(acc, p);
+  }
+  partial[t] = acc;
+}
+
+// ---------------------------------------------------------------- 6 finalize
+template <class F>
+B381_DI void msm_finalize_body(uint32_t b, uint32_t nbuckets, const uint32_t* task_start,
+                               const uint32_t* counts, const xyzz_t<F>* partial, xyzz_t<F>* buckets) {
+  if (b >= nbuckets) return;
+  uint32_t t0 = task_start[b], nt = counts[b];
+  xyzz_t<F> acc = xyzz_identity<F>();
+  if (nt) acc = partial[t0];
+  for (uint32_t t = 1; t < nt; t++) xyzz_add(acc, partial[t0 + t]);
+  buckets[b] = acc;
+}
+
+// ---------------------------------------------------------------- 7 segment reduce
+// window w, segment s covers buckets j = s*L .. s*L+L-1 (weights j+1).
+//   sum_j (j+1) B_j = T_s + (s*L) * A_s,   A_s = sum B_j,  T_s = sum (j-s*L+1) B_j
+template <class F>
+B381_DI xyzz_t<F> xyzz_mul_small(const xyzz_t<F>& p, uint32_t k) {
+  xyzz_t<F> r = xyzz_identity<F>();
+  if (k == 0 || is_inf(p)) return r;
+  int top = 31;
+  while (!((k >> top) & 1)) top--;
+  for (int i = top; i >= 0; i--) {
+    r = xyzz_dbl(r);
+    if ((k >> i) & 1) xyzz_add(r, p);
+  }
+  return r;
+}
+
+template <class F>
+B381_DI void msm_segment_body(uint32_t gid, uint32_t W, uint32_t B, uint32_t L, const xyzz_t<F>* buckets,
+                              xyzz_t<F>* seg_out) {
+  uint32_t segs = B / L;
+  if (gid >= W * segs) return;
+  uint32_t w = gid / segs, s = gid % segs;
+  const xyzz_t<F>* bk = buckets + (size_t)w * B + (size_t)s * L;
+  xyzz_t<F> run = xyzz_identity<F>();
+  xyzz_t<F> tri = xyzz_identity<F>();
+  for (int j = (int)L - 1; j >= 0; j--) {
+    xyzz_add(run, bk[j]);
+    xyzz_add(tri, run);
+  }
+  xyzz_t<F> sh = xyzz_mul_small(run, s * L);
+  xyzz_add(tri, sh);
+  seg_out[gid] = tri;
+}
+
+// ---------------------------------------------------------------- 8 tree
+// in-place halving over groups: a[g*stride + t] += a[g*stride + t + half]
+template <class F>
+B381_DI void msm_tree_body(uint32_t gid, uint32_t groups, uint32_t stride, uint32_t half, xyzz_t<F>* a) {
+  if (gid >= groups * half) return;
+  uint32_t g = gid / half, t = gid % half;
+  xyzz_t<F> x = a[(size_t)g * stride + t];
+  xyzz_add(x, a[(size_t)g * stride + t + half]);
+  a[(size_t)g * stride + t] = x;
+}
+
+// ---------------------------------------------------------------- 9 combine
+// Horner over the W window sums (stride apart), result left in XYZZ.
+template <class F>
+B381_DI xyzz_t<F> msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c) {
+  xyzz_t<F> r = xyzz_identity<F>();
+  for (int w = (int)W - 1; w >= 0; w--) {
+    for (uint32_t k = 0; k < c; k++) r = xyzz_dbl(r);
+    xyzz_add(r, wsum[(size_t)w * stride]);
+  }
+  return r;
+}
+
+// ICICLE result convention (icicle_curve_api.cu:134-179): (x, y, 1) in STANDARD form,
+// identity = (0, 1, 0).  With `mont` the coordinates stay Montgomery and identity = (0, R, 0),
+// which is the reference's Jacobian convention (point.cuh:469-486) for its extern "C" test API.
+template <class F>
+B381_DI jacobian_t<F> msm_result_encode(const xyzz_t<F>& r, bool mont) {
+  affine_t<F> a = xyzz_to_affine(r);
+  jacobian_t<F> o;
+  if (is_inf(r)) {
+    o.x = zero<F>();
+    o.y = one<F>();
+    o.z = zero<F>();
+  } else {
+    o.x = a.x;
+    o.y = a.y;
+    o.z = one<F>();
+  }
+  if (!mont) {
+    o.x = from_mont(o.x);
+    o.y = from_mont(o.y);
+    o.z = from_mont(o.z);
+  }
+  return o;
+}
+
+}  // namespace b381

@@ -1,0 +1,66 @@
+// CPU-only driver for the per-thread MSM bodies in csrc/msm_core.cuh (TEST INFRASTRUCTURE).
+// Runs exactly the kernel pipeline of csrc/msm.cu with a serial loop per "kernel" and
+// std::stable_sort in place of the device radix sort.  Usage:
+//   msm_host_sim <g1|g2> <n> <c> <K> <L> <scalars_mont 0|1> <infile> ; prints result hex (std form)
+// infile = n*32 B scalars followed by n*(96|192) B Montgomery affine points.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <numeric>
+#include <vector>
+#define B381_HOST_TEST 1
+#include "msm_core.cuh"
+using namespace b381;
+
+template <class F>
+int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f) {
+  std::vector<fr_t> sc(n);
+  std::vector<affine_t<F>> pts(n);
+  if (fread(sc.data(), sizeof(fr_t), n, f) != n) return 2;
+  if (fread(pts.data(), sizeof(affine_t<F>), n, f) != n) return 2;
+  msm_shape sh;
+  sh.n = n; sh.c = c; sh.W = (256 + c - 1) / c; sh.B = 1u << (c - 1); sh.nbuckets = sh.W * sh.B;
+  size_t total = (size_t)n * sh.W;
+  std::vector<uint32_t> keys(total), vals(total);
+  for (uint32_t i = 0; i < n; i++) msm_digits_body(i, sc.data(), mont, sh, keys.data(), vals.data());
+  std::vector<size_t> perm(total);
+  std::iota(perm.begin(), perm.end(), 0);
+  std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+  std::vector<uint32_t> sk(total), sv(total);
+  for (size_t j = 0; j < total; j++) { sk[j] = keys[perm[j]]; sv[j] = vals[perm[j]]; }
+  std::vector<uint32_t> offsets(sh.nbuckets + 1, 0xdeadbeef);
+  for (size_t j = 0; j <= total; j++) msm_offsets_body(j, sk.data(), total, sh.nbuckets, offsets.data());
+  std::vector<uint32_t> counts(sh.nbuckets), tstart(sh.nbuckets);
+  for (uint32_t b = 0; b < sh.nbuckets; b++) msm_task_count_body(b, offsets.data(), sh.nbuckets, K, counts.data());
+  uint32_t ntasks = 0;
+  for (uint32_t b = 0; b < sh.nbuckets; b++) { tstart[b] = ntasks; ntasks += counts[b]; }
+  std::vector<uint2> tasks(ntasks ? ntasks : 1);
+  for (uint32_t b = 0; b < sh.nbuckets; b++) msm_build_tasks_body(b, offsets.data(), tstart.data(), sh.nbuckets, K, tasks.data());
+  std::vector<xyzz_t<F>> partial(ntasks ? ntasks : 1), buckets(sh.nbuckets);
+  for (uint32_t t = 0; t < ntasks; t++) msm_accumulate_body<F>(t, ntasks, tasks.data(), sv.data(), pts.data(), partial.data());
+  for (uint32_t b = 0; b < sh.nbuckets; b++) msm_finalize_body<F>(b, sh.nbuckets, tstart.data(), counts.data(), partial.data(), buckets.data());
+  if (L > sh.B) L = sh.B;
+  uint32_t segs = sh.B / L;
+  std::vector<xyzz_t<F>> seg(sh.W * segs);
+  for (uint32_t g = 0; g < sh.W * segs; g++) msm_segment_body<F>(g, sh.W, sh.B, L, buckets.data(), seg.data());
+  for (uint32_t half = segs / 2; half >= 1; half /= 2)
+    for (uint32_t g = 0; g < sh.W * half; g++) msm_tree_body<F>(g, sh.W, segs, half, seg.data());
+  xyzz_t<F> r = msm_combine<F>(seg.data(), segs, sh.W, sh.c);
+  jacobian_t<F> o = msm_result_encode<F>(r, false);
+  const unsigned char* p = (const unsigned char*)&o;
+  for (size_t i = 0; i < sizeof(o); i++) printf("%02x", p[i]);
+  printf("\n");
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc < 8) return 1;
+  bool g2 = argv[1][1] == '2';
+  uint32_t n = atoi(argv[2]), c = atoi(argv[3]), K = atoi(argv[4]), L = atoi(argv[5]);
+  bool mont = atoi(argv[6]) != 0;
+  FILE* f = fopen(argv[7], "rb");
+  if (!f) return 3;
+  int rc = g2 ? run<fq2_t>(n, c, K, L, mont, f) : run<fq_t>(n, c, K, L, mont, f);
+  fclose(f);
+  return rc;
+}
