@@ -1,0 +1,97 @@
+// Host-side plumbing shared by the .cu translation units: error mapping, stream-ordered
+// scratch memory and residency staging.  (The reference cudaMalloc/cudaFree's up to 11 buffers
+// per MSM call and maps every failure to ALLOCATION_FAILED -- src/curve/msm_kernels.cu:705-719,
+// include/icicle_types.cuh:41-45; here scratch comes from the stream-ordered pool, so a call
+// never implicitly synchronises the device.)
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/b381.h"
+
+namespace b381 {
+
+inline int map_cuda_error(cudaError_t e) {
+  switch (e) {
+    case cudaSuccess: return B381_SUCCESS;
+    case cudaErrorMemoryAllocation: return B381_OUT_OF_MEMORY;
+    case cudaErrorInvalidValue: return B381_INVALID_ARGUMENT;
+    case cudaErrorInvalidDevice:
+    case cudaErrorNoDevice:
+    case cudaErrorInsufficientDriver: return B381_INVALID_DEVICE;
+    default: return B381_UNKNOWN_ERROR;
+  }
+}
+
+#define B381_CUDA_TRY(expr)                                                            \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      if (getenv("B381_DEBUG"))                                                        \
+        fprintf(stderr, "[b381] %s:%d %s -> %s\n", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return _e;                                                                       \
+    }                                                                                  \
+  } while (0)
+
+// Keep freed scratch cached in the default pool instead of returning it to the driver.
+inline void configure_pool_once() {
+  static bool done = false;
+  if (done) return;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  done = true;
+}
+
+// RAII bag of stream-ordered allocations; everything is released (asynchronously, in stream
+// order) when the bag dies, so is_async callers return without a host sync.
+class Scratch {
+ public:
+  explicit Scratch(cudaStream_t s) : s_(s) { configure_pool_once(); }
+  ~Scratch() {
+    for (void* p : ptrs_) cudaFreeAsync(p, s_);
+  }
+  template <class T>
+  cudaError_t alloc(T** out, size_t count) {
+    void* p = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMallocAsync(&p, bytes, s_);
+    if (e != cudaSuccess) return e;
+    ptrs_.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    return cudaSuccess;
+  }
+  cudaStream_t stream() const { return s_; }
+
+ private:
+  cudaStream_t s_;
+  std::vector<void*> ptrs_;
+};
+
+// Device view of a caller buffer: used in place when it already lives on the device, else
+// copied into scratch on the stream.
+template <class T>
+cudaError_t stage_in(Scratch& sc, const T* src, size_t count, bool on_device, const T** out) {
+  if (on_device) {
+    *out = src;
+    return cudaSuccess;
+  }
+  T* d = nullptr;
+  cudaError_t e = sc.alloc(&d, count);
+  if (e != cudaSuccess) return e;
+  e = cudaMemcpyAsync(d, src, count * sizeof(T), cudaMemcpyHostToDevice, sc.stream());
+  *out = d;
+  return e;
+}
+
+inline unsigned grid_for(size_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
+
+}  // namespace b381

@@ -12,9 +12,11 @@
 #include "field_host_shim.h"
 #include "field_consts.h"
 #define B381_DI inline
+#define B381_HD inline
 #else
 #include "field_ptx.cuh"
 #define B381_DI __device__ __forceinline__
+#define B381_HD __host__ __device__ __forceinline__
 #endif
 
 namespace b381 {

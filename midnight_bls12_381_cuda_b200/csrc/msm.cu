@@ -1,0 +1,440 @@
+// Pippenger MSM for BLS12-381 G1 and G2 on sm_100a: kernels + host driver + C ABI.
+// Kernel bodies live in msm_core.cuh (host-testable); pipeline description there.
+//
+// Replaces: msm::msm_cuda<S,A,P> (bls12-381/src/curve/msm_kernels.cu:603-903) and the ICICLE
+// wrappers msm_cuda_impl / msm_g2_cuda_impl / msm_precompute_bases_cuda_impl
+// (bls12-381/src/backend/icicle_curve_api.cu:243-407, :415-440, :454-650).
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "msm_core.cuh"
+
+namespace b381 {
+
+// ------------------------------------------------------------------ kernels
+__global__ void k_msm_digits(const fr_t* scalars, bool mont, msm_shape sh, uint32_t* keys, uint32_t* vals) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_digits_body(i, scalars, mont, sh, keys, vals);
+}
+
+__global__ void k_msm_offsets(const uint32_t* sorted_keys, size_t total, uint32_t nbuckets, uint32_t* offsets) {
+  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  msm_offsets_body(j, sorted_keys, total, nbuckets, offsets);
+}
+
+__global__ void k_msm_task_count(const uint32_t* offsets, uint32_t nbuckets, uint32_t K, uint32_t* counts) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == nbuckets) counts[b] = 0;  // sentinel so the exclusive scan yields the task total
+  msm_task_count_body(b, offsets, nbuckets, K, counts);
+}
+
+__global__ void k_msm_build_tasks(const uint32_t* offsets, const uint32_t* task_start, uint32_t nbuckets,
+                                  uint32_t K, uint2* tasks) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_build_tasks_body(b, offsets, task_start, nbuckets, K, tasks);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* ntasks_dev, const uint2* tasks,
+                                                        const uint32_t* sorted_vals, const affine_t<F>* bases,
+                                                        xyzz_t<F>* partial) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_accumulate_body<F>(t, *ntasks_dev, tasks, sorted_vals, bases, partial);
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_finalize(uint32_t nbuckets, const uint32_t* task_start,
+                                                      const uint32_t* counts, const xyzz_t<F>* partial,
+                                                      xyzz_t<F>* buckets) {
+  uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_finalize_body<F>(b, nbuckets, task_start, counts, partial, buckets);
+}
+
+template <class F>
+__global__ void __launch_bounds__(64) k_msm_segment(uint32_t W, uint32_t B, uint32_t L, const xyzz_t<F>* buckets,
+                                                    xyzz_t<F>* seg_out) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_segment_body<F>(g, W, B, L, buckets, seg_out);
+}
+
+template <class F>
+__global__ void __launch_bounds__(64) k_msm_tree(uint32_t groups, uint32_t stride, uint32_t half, xyzz_t<F>* a) {
+  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_tree_body<F>(g, groups, stride, half, a);
+}
+
+template <class F>
+__global__ void k_msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c, xyzz_t<F>* out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = msm_combine<F>(wsum, stride, W, c);
+}
+
+template <class F>
+__global__ void k_msm_set_identity(xyzz_t<F>* out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = xyzz_identity<F>();
+}
+
+// sum `count` XYZZ partials and encode the ICICLE result
+template <class F>
+__global__ void k_msm_encode(const xyzz_t<F>* parts, int count, bool mont, jacobian_t<F>* out) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  xyzz_t<F> acc = xyzz_identity<F>();
+  for (int i = 0; i < count; i++) xyzz_add(acc, parts[i]);
+  *out = msm_result_encode<F>(acc, mont);
+}
+
+template <class F>
+__global__ void k_points_to_mont(const affine_t<F>* in, affine_t<F>* out, uint32_t n) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  affine_t<F> p = in[i];
+  out[i] = affine_t<F>{to_mont(p.x), to_mont(p.y)};
+}
+
+// out[k*n + i] = 2^(k*shift_bits) * in[i]  (affine Montgomery), one thread per input point.
+template <class F>
+__global__ void __launch_bounds__(64) k_precompute_bases(const affine_t<F>* in, affine_t<F>* out, uint32_t n,
+                                                         uint32_t factor, uint32_t shift_bits) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  affine_t<F> p = in[i];
+  out[i] = p;
+  xyzz_t<F> acc = to_xyzz(p);
+  for (uint32_t k = 1; k < factor; k++) {
+    for (uint32_t b = 0; b < shift_bits; b++) acc = xyzz_dbl(acc);
+    out[(size_t)k * n + i] = xyzz_to_affine(acc);
+  }
+}
+
+// ------------------------------------------------------------------ host driver
+static thread_local float g_last_timings[8];
+static thread_local int g_last_timings_n = 0;
+
+struct PhaseTimer {
+  bool on;
+  cudaStream_t s;
+  std::vector<cudaEvent_t> ev;
+  PhaseTimer(cudaStream_t st) : s(st) {
+    const char* e = getenv("B381_MSM_TIMING");
+    on = e && e[0] == '1';
+  }
+  void mark() {
+    if (!on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    ev.push_back(e);
+  }
+  void finish() {
+    if (!on || ev.empty()) return;
+    cudaEventSynchronize(ev.back());
+    g_last_timings_n = 0;
+    for (size_t i = 1; i < ev.size() && g_last_timings_n < 8; i++)
+      cudaEventElapsedTime(&g_last_timings[g_last_timings_n++], ev[i - 1], ev[i]);
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+  }
+};
+
+static uint32_t ceil_log2_u64(uint64_t v) {
+  uint32_t b = 0;
+  while ((1ull << b) < v) b++;
+  return b;
+}
+
+// Window size: minimise  W * (10 n + 36 * 2^(c-1))  Fq-mul equivalents (bucket insertions +
+// bucket reduction), W = ceil((bits+1)/c).  Replaces get_optimal_c (include/msm.cuh:115-140).
+static uint32_t pick_window(uint32_t n, uint32_t bits, uint32_t factor) {
+  const char* e = getenv("B381_MSM_C");
+  if (e && atoi(e) > 0) return (uint32_t)atoi(e);
+  double best = 1e300;
+  uint32_t bc = 4;
+  for (uint32_t c = 4; c <= 22; c++) {
+    uint32_t W = (bits + 1 + c - 1) / c;
+    uint32_t Wf = (W + factor - 1) / factor;
+    double cost = (double)W * 10.0 * n + (double)Wf * 36.0 * (double)(1u << (c - 1));
+    if (cost < best) { best = cost; bc = c; }
+  }
+  return bc;
+}
+
+template <class F>
+static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const affine_t<F>* d_bases,
+                              uint32_t n, uint32_t c_req, uint32_t bits, uint32_t factor, xyzz_t<F>* d_out) {
+  cudaStream_t st = sc.stream();
+  if (n == 0) {
+    k_msm_set_identity<F><<<1, 1, 0, st>>>(d_out);
+    return cudaGetLastError();
+  }
+  PhaseTimer tm(st);
+  uint32_t c = c_req ? c_req : pick_window(n, bits, factor);
+  if (c < 2) c = 2;
+  if (c > 24) c = 24;
+  const msm_shape sh = make_msm_shape(n, c, bits, factor);
+  if ((uint64_t)n * factor >= (1ull << 31)) return cudaErrorInvalidValue;
+  const size_t total = (size_t)n * sh.W;
+  if (total >= (1ull << 31)) return cudaErrorInvalidValue;
+
+  // -- 1 digits
+  uint32_t *keys[2], *vals[2];
+  for (int i = 0; i < 2; i++) {
+    B381_CUDA_TRY(sc.alloc(&keys[i], total));
+    B381_CUDA_TRY(sc.alloc(&vals[i], total));
+  }
+  tm.mark();
+  k_msm_digits<<<grid_for(n, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, keys[0], vals[0]);
+  tm.mark();
+
+  // -- 2 sort (only the significant key bits)
+  cub::DoubleBuffer<uint32_t> dk(keys[0], keys[1]), dv(vals[0], vals[1]);
+  int key_bits = (int)ceil_log2_u64((uint64_t)sh.nbuckets + 1);
+  size_t tmp_bytes = 0;
+  B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)total, 0, key_bits, st));
+  uint8_t* tmp = nullptr;
+  B381_CUDA_TRY(sc.alloc(&tmp, tmp_bytes));
+  B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)total, 0, key_bits, st));
+  const uint32_t* skeys = dk.Current();
+  const uint32_t* svals = dv.Current();
+  tm.mark();
+
+  // -- 3 offsets, 4 tasks
+  uint32_t *offsets, *counts, *task_start;
+  B381_CUDA_TRY(sc.alloc(&offsets, (size_t)sh.nbuckets + 1));
+  B381_CUDA_TRY(sc.alloc(&counts, (size_t)sh.nbuckets + 1));
+  B381_CUDA_TRY(sc.alloc(&task_start, (size_t)sh.nbuckets + 1));
+  k_msm_offsets<<<grid_for(total + 1, 256), 256, 0, st>>>(skeys, total, sh.nbuckets, offsets);
+  // task length bound: mean bucket load + 4 sigma (Poisson), so a uniform input is one task per bucket
+  double avg = (double)n / (double)sh.B;
+  uint32_t K = (uint32_t)(avg + 4.0 * sqrt(avg) + 8.0);
+  {
+    const char* e = getenv("B381_MSM_K");
+    if (e && atoi(e) > 0) K = (uint32_t)atoi(e);
+  }
+  k_msm_task_count<<<grid_for((size_t)sh.nbuckets + 1, 256), 256, 0, st>>>(offsets, sh.nbuckets, K, counts);
+  size_t scan_bytes = 0;
+  B381_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, task_start, (int)sh.nbuckets + 1, st));
+  uint8_t* scan_tmp = nullptr;
+  B381_CUDA_TRY(sc.alloc(&scan_tmp, scan_bytes));
+  B381_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, counts, task_start, (int)sh.nbuckets + 1, st));
+  const size_t max_tasks = (size_t)sh.nbuckets + total / K + 1;
+  uint2* tasks;
+  B381_CUDA_TRY(sc.alloc(&tasks, max_tasks));
+  k_msm_build_tasks<<<grid_for(sh.nbuckets, 256), 256, 0, st>>>(offsets, task_start, sh.nbuckets, K, tasks);
+  tm.mark();
+
+  // -- 5 accumulate
+  xyzz_t<F>*partial, *buckets;
+  B381_CUDA_TRY(sc.alloc(&partial, max_tasks));
+  B381_CUDA_TRY(sc.alloc(&buckets, (size_t)sh.nbuckets));
+  k_msm_accumulate<F><<<grid_for(max_tasks, 128), 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial);
+  tm.mark();
+  // -- 6 finalize
+  k_msm_finalize<F><<<grid_for(sh.nbuckets, 128), 128, 0, st>>>(sh.nbuckets, task_start, counts, partial, buckets);
+  tm.mark();
+
+  // -- 7 segments, 8 tree
+  uint32_t L = 32;
+  {
+    const char* e = getenv("B381_MSM_L");
+    if (e && atoi(e) > 0) L = (uint32_t)atoi(e);
+  }
+  while (L > sh.B) L >>= 1;
+  uint32_t segs = sh.B / L;
+  xyzz_t<F>* seg;
+  B381_CUDA_TRY(sc.alloc(&seg, (size_t)sh.Wf * segs));
+  k_msm_segment<F><<<grid_for((size_t)sh.Wf * segs, 64), 64, 0, st>>>(sh.Wf, sh.B, L, buckets, seg);
+  for (uint32_t half = segs / 2; half >= 1; half >>= 1)
+    k_msm_tree<F><<<grid_for((size_t)sh.Wf * half, 64), 64, 0, st>>>(sh.Wf, segs, half, seg);
+  tm.mark();
+  // -- 9 combine
+  k_msm_combine<F><<<1, 1, 0, st>>>(seg, segs, sh.Wf, sh.c, d_out);
+  tm.mark();
+  B381_CUDA_TRY(cudaGetLastError());
+  tm.finish();
+  return cudaSuccess;
+}
+
+enum class ResultKind { IcicleStd, JacobianMont, PartialXyzz };
+
+template <class F>
+static int msm_entry(const fr_t* scalars, const affine_t<F>* bases, int msm_size, const b381_msm_config* cfg,
+                     void* results, ResultKind kind) {
+  if (!cfg || !results) return B381_INVALID_POINTER;
+  if (msm_size < 0) return B381_INVALID_ARGUMENT;
+  if (msm_size > 0 && (!scalars || !bases)) return B381_INVALID_POINTER;
+  int batch = cfg->batch_size > 0 ? cfg->batch_size : 1;
+  if (cfg->c < 0 || cfg->c > 24) return B381_INVALID_ARGUMENT;
+  if (cfg->bitsize < 0 || cfg->bitsize > 256) return B381_INVALID_ARGUMENT;
+  uint32_t bits = cfg->bitsize > 0 ? (uint32_t)cfg->bitsize : 255u;
+  uint32_t n = (uint32_t)msm_size;
+  cudaStream_t st = (cudaStream_t)cfg->stream;
+  cudaError_t e;
+  {
+    Scratch sc(st);
+    const fr_t* d_scalars = nullptr;
+    const affine_t<F>* d_bases = nullptr;
+    uint32_t factor = cfg->precompute_factor > 1 ? (uint32_t)cfg->precompute_factor : 1u;
+    size_t nbases = (cfg->are_points_shared_in_batch ? (size_t)n : (size_t)n * batch) * factor;
+    if ((e = stage_in(sc, scalars, (size_t)n * batch, cfg->are_scalars_on_device, &d_scalars)) != cudaSuccess)
+      return map_cuda_error(e);
+    if ((e = stage_in(sc, bases, nbases, cfg->are_points_on_device, &d_bases)) != cudaSuccess)
+      return map_cuda_error(e);
+    if (!cfg->are_points_montgomery_form && nbases) {
+      affine_t<F>* conv;
+      if ((e = sc.alloc(&conv, nbases)) != cudaSuccess) return map_cuda_error(e);
+      k_points_to_mont<F><<<grid_for(nbases, 128), 128, 0, st>>>(d_bases, conv, (uint32_t)nbases);
+      d_bases = conv;
+    }
+    xyzz_t<F>* d_part;
+    if ((e = sc.alloc(&d_part, (size_t)batch)) != cudaSuccess) return map_cuda_error(e);
+    for (int b = 0; b < batch; b++) {
+      const affine_t<F>* bb = cfg->are_points_shared_in_batch ? d_bases : d_bases + (size_t)b * n * factor;
+      e = msm_single<F>(sc, d_scalars + (size_t)b * n, cfg->are_scalars_montgomery_form, bb, n, (uint32_t)cfg->c,
+                        bits, factor, d_part + b);
+      if (e != cudaSuccess) return map_cuda_error(e);
+    }
+    if (kind == ResultKind::PartialXyzz) {
+      // caller's buffer is device memory by contract
+      e = cudaMemcpyAsync(results, d_part, sizeof(xyzz_t<F>) * batch, cudaMemcpyDeviceToDevice, st);
+      if (e != cudaSuccess) return map_cuda_error(e);
+    } else {
+      jacobian_t<F>* d_res;
+      bool direct = cfg->are_results_on_device;
+      if (direct) d_res = reinterpret_cast<jacobian_t<F>*>(results);
+      else if ((e = sc.alloc(&d_res, (size_t)batch)) != cudaSuccess) return map_cuda_error(e);
+      for (int b = 0; b < batch; b++)
+        k_msm_encode<F><<<1, 1, 0, st>>>(d_part + b, 1, kind == ResultKind::JacobianMont, d_res + b);
+      if (!direct) {
+        e = cudaMemcpyAsync(results, d_res, sizeof(jacobian_t<F>) * batch, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) return map_cuda_error(e);
+      }
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return map_cuda_error(e);
+  }  // scratch released in stream order
+  if (!cfg->is_async) {
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return map_cuda_error(e);
+  }
+  return B381_SUCCESS;
+}
+
+template <class F>
+static int precompute_entry(const affine_t<F>* in, int bases_size, const b381_msm_config* cfg, affine_t<F>* out) {
+  if (!cfg || !in || !out) return B381_INVALID_POINTER;
+  if (bases_size < 0) return B381_INVALID_ARGUMENT;
+  uint32_t n = (uint32_t)bases_size;
+  uint32_t factor = cfg->precompute_factor > 1 ? (uint32_t)cfg->precompute_factor : 1u;
+  cudaStream_t st = (cudaStream_t)cfg->stream;
+  cudaError_t e;
+  {
+    Scratch sc(st);
+    const affine_t<F>* d_in = nullptr;
+    if ((e = stage_in(sc, in, n, cfg->are_points_on_device, &d_in)) != cudaSuccess) return map_cuda_error(e);
+    if (!cfg->are_points_montgomery_form && n) {
+      affine_t<F>* conv;
+      if ((e = sc.alloc(&conv, (size_t)n)) != cudaSuccess) return map_cuda_error(e);
+      k_points_to_mont<F><<<grid_for(n, 128), 128, 0, st>>>(d_in, conv, n);
+      d_in = conv;
+    }
+    // results live where cfg says (ICICLE: are_results_on_device)
+    affine_t<F>* d_out = out;
+    if (!cfg->are_results_on_device) {
+      if ((e = sc.alloc(&d_out, (size_t)n * factor)) != cudaSuccess) return map_cuda_error(e);
+    }
+    uint32_t bits = cfg->bitsize > 0 ? (uint32_t)cfg->bitsize : 255u;
+    uint32_t c = cfg->c > 0 ? (uint32_t)cfg->c : pick_window(n, bits, factor);
+    const msm_shape sh = make_msm_shape(n, c, bits, factor);
+    uint32_t shift = c * sh.Wf;
+    if (n) k_precompute_bases<F><<<grid_for(n, 64), 64, 0, st>>>(d_in, d_out, n, factor, shift);
+    if (!cfg->are_results_on_device) {
+      e = cudaMemcpyAsync(out, d_out, sizeof(affine_t<F>) * (size_t)n * factor, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return map_cuda_error(e);
+    }
+    if ((e = cudaGetLastError()) != cudaSuccess) return map_cuda_error(e);
+  }
+  if (!cfg->is_async) {
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return map_cuda_error(e);
+  }
+  return B381_SUCCESS;
+}
+
+template <class F>
+static int combine_entry(const void* parts, int count, void* stream, bool on_device, void* result) {
+  if (!parts || !result || count < 0) return B381_INVALID_ARGUMENT;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e;
+  {
+    Scratch sc(st);
+    jacobian_t<F>* d_res = reinterpret_cast<jacobian_t<F>*>(result);
+    if (!on_device && (e = sc.alloc(&d_res, 1)) != cudaSuccess) return map_cuda_error(e);
+    k_msm_encode<F><<<1, 1, 0, st>>>(reinterpret_cast<const xyzz_t<F>*>(parts), count, false, d_res);
+    if (!on_device) {
+      e = cudaMemcpyAsync(result, d_res, sizeof(jacobian_t<F>), cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return map_cuda_error(e);
+    }
+  }
+  e = cudaStreamSynchronize(st);
+  return map_cuda_error(e);
+}
+
+}  // namespace b381
+
+using namespace b381;
+
+static_assert(sizeof(b381_g1_affine) == sizeof(g1_affine) && sizeof(b381_g2_affine) == sizeof(g2_affine), "layout");
+static_assert(sizeof(b381_g1_projective) == sizeof(g1_jac) && sizeof(b381_g2_projective) == sizeof(g2_jac), "layout");
+static_assert(sizeof(b381_fr) == sizeof(fr_t), "layout");
+
+extern "C" {
+
+int b381_g1_msm(const b381_fr* s, const b381_g1_affine* p, int n, const b381_msm_config* cfg, b381_g1_projective* r) {
+  return msm_entry<fq_t>((const fr_t*)s, (const g1_affine*)p, n, cfg, r, ResultKind::IcicleStd);
+}
+int b381_g2_msm(const b381_fr* s, const b381_g2_affine* p, int n, const b381_msm_config* cfg, b381_g2_projective* r) {
+  return msm_entry<fq2_t>((const fr_t*)s, (const g2_affine*)p, n, cfg, r, ResultKind::IcicleStd);
+}
+int bls12_381_g1_msm_cuda(const b381_fr* s, const b381_g1_affine* p, int n, const b381_msm_config* cfg,
+                          b381_g1_projective* r) {
+  return msm_entry<fq_t>((const fr_t*)s, (const g1_affine*)p, n, cfg, r, ResultKind::JacobianMont);
+}
+int bls12_381_g2_msm_cuda(const b381_fr* s, const b381_g2_affine* p, int n, const b381_msm_config* cfg,
+                          b381_g2_projective* r) {
+  return msm_entry<fq2_t>((const fr_t*)s, (const g2_affine*)p, n, cfg, r, ResultKind::JacobianMont);
+}
+int b381_g1_msm_partial(const b381_fr* s, const b381_g1_affine* p, int n, const b381_msm_config* cfg, void* out) {
+  return msm_entry<fq_t>((const fr_t*)s, (const g1_affine*)p, n, cfg, out, ResultKind::PartialXyzz);
+}
+int b381_g2_msm_partial(const b381_fr* s, const b381_g2_affine* p, int n, const b381_msm_config* cfg, void* out) {
+  return msm_entry<fq2_t>((const fr_t*)s, (const g2_affine*)p, n, cfg, out, ResultKind::PartialXyzz);
+}
+int b381_g1_msm_combine(const void* parts, int count, void* stream, bool on_device, b381_g1_projective* r) {
+  return combine_entry<fq_t>(parts, count, stream, on_device, r);
+}
+int b381_g2_msm_combine(const void* parts, int count, void* stream, bool on_device, b381_g2_projective* r) {
+  return combine_entry<fq2_t>(parts, count, stream, on_device, r);
+}
+int b381_g1_msm_precompute_bases(const b381_g1_affine* in, int n, const b381_msm_config* cfg, b381_g1_affine* out) {
+  return precompute_entry<fq_t>((const g1_affine*)in, n, cfg, (g1_affine*)out);
+}
+int b381_g2_msm_precompute_bases(const b381_g2_affine* in, int n, const b381_msm_config* cfg, b381_g2_affine* out) {
+  return precompute_entry<fq2_t>((const g2_affine*)in, n, cfg, (g2_affine*)out);
+}
+int b381_msm_last_timings(float* out, int cap) {
+  int k = g_last_timings_n < cap ? g_last_timings_n : cap;
+  for (int i = 0; i < k; i++) out[i] = g_last_timings[i];
+  return k;
+}
+b381_msm_config b381_default_msm_config(void) {
+  b381_msm_config c;
+  memset(&c, 0, sizeof(c));
+  c.precompute_factor = 1;
+  c.batch_size = 1;
+  c.are_points_shared_in_batch = true;
+  return c;
+}
+
+}  // extern "C"

@@ -28,12 +28,28 @@ namespace b381 {
 struct msm_shape {
   uint32_t n;        // points in this MSM
   uint32_t c;        // window bits
-  uint32_t W;        // number of windows
+  uint32_t W;        // number of c-bit windows of the scalar
   uint32_t B;        // buckets per window = 2^(c-1)
-  uint32_t nbuckets; // W*B  (key W*B is the trash key)
+  uint32_t Wf;       // bucket sets after folding with precomputed bases: ceil(W / precompute_factor)
+  uint32_t nbuckets; // Wf*B  (key Wf*B is the trash key)
 };
 
-B381_DI uint32_t ceil_div_u32(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+// With precompute_factor f the caller supplies f*n bases, block k holding 2^(k*Wf*c) * P_i, and
+// window w = k*Wf + w' is inserted into bucket set w' using base block k -- all windows of one
+// residue class share buckets, so only Wf bucket sets are reduced and combined.
+B381_HD msm_shape make_msm_shape(uint32_t n, uint32_t c, uint32_t bits, uint32_t factor) {
+  msm_shape sh;
+  sh.n = n;
+  sh.c = c;
+  sh.W = (bits + 1 + c - 1) / c;
+  sh.B = 1u << (c - 1);
+  if (factor < 1) factor = 1;
+  sh.Wf = (sh.W + factor - 1) / factor;
+  sh.nbuckets = sh.Wf * sh.B;
+  return sh;
+}
+
+B381_HD uint32_t ceil_div_u32(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------- 1 digits
 // Signed-digit recoding with the same digit set as the reference
@@ -63,9 +79,10 @@ B381_DI void msm_digits_body(uint32_t i, const fr_t* scalars, bool scalars_mont,
       sign = 1;
       carry = 1;
     }
-    uint32_t key = d ? (w * sh.B + d - 1) : sh.nbuckets;
+    uint32_t blk = w / sh.Wf, wf = w - blk * sh.Wf;
+    uint32_t key = d ? (wf * sh.B + d - 1) : sh.nbuckets;
     keys[(size_t)w * sh.n + i] = key;
-    vals[(size_t)w * sh.n + i] = (i << 1) | sign;
+    vals[(size_t)w * sh.n + i] = ((blk * sh.n + i) << 1) | sign;
   }
   // W*c >= 256 > bit length of any canonical scalar, so the last carry is always 0.
 }

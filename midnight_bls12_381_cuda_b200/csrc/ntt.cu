@@ -1,0 +1,330 @@
+// Fr NTT / iNTT for sm_100a: domain (twiddle) management, pass planner, kernels, C ABI.
+// Butterfly bodies are in ntt_core.cuh.
+//
+// Replaces: init_domain_cuda_impl / release_domain_cuda_impl / ntt_cuda_impl / coset_ntt_cuda_impl
+// (bls12-381/src/field/ntt_kernels.cu:1607-1679, :1823-1848, :968-1133, :1155-1306) and the
+// wrappers in bls12-381/src/backend/icicle_field_api.cu:97-131.
+#include <cstring>
+#include <map>
+#include <mutex>
+
+#include "common.cuh"
+#include "ntt_core.cuh"
+
+namespace b381 {
+
+constexpr uint32_t kTile = 1u << kNttTileLog;
+constexpr uint32_t kNttThreads = 256;
+constexpr uint32_t kMaxDomainLog = 28;            // 2^28 - 1 twiddles = 8 GiB; larger roots are refused
+
+// ------------------------------------------------------------------ kernels
+__global__ void __launch_bounds__(kNttThreads, 3) k_ntt_pass(ntt_pass_params p, const fr_t* in, fr_t* out) {
+  extern __shared__ uint4 smem[];
+  ntt_tile t;
+  const uint32_t tile_elems = 1u << (p.S + p.g + p.x);
+  t.lo = smem;
+  t.hi = smem + tile_elems;
+  const uint64_t tile_id = blockIdx.x;
+  for (uint32_t pos = threadIdx.x; pos < tile_elems; pos += blockDim.x) ntt_tile_load(p, tile_id, pos, in, t);
+  __syncthreads();
+  for (int s = (int)p.S - 1; s >= 0; s--) {
+    for (uint32_t q = threadIdx.x; q < tile_elems / 2; q += blockDim.x) ntt_tile_stage(p, tile_id, q, (uint32_t)s, t);
+    __syncthreads();
+  }
+  for (uint32_t pos = threadIdx.x; pos < tile_elems; pos += blockDim.x) ntt_tile_store(p, tile_id, pos, out, t);
+}
+
+// out[j] = base * g^j, j < count, 64 consecutive powers per thread
+__global__ void k_fr_powers(fr_t g, fr_t base, uint64_t count, fr_t* out) {
+  uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  fr_powers_chunk(chunk, 64, count, g, base, out);
+}
+
+// stage-major table from the top-level powers: T[2^k - 1 + j] = top[j << (K-1-k)]
+__global__ void k_twiddle_subsample(const fr_t* top, uint32_t K, fr_t* table) {
+  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;   // 0 .. 2^(K-1)-2 : all levels below the top
+  uint64_t lim = (1ull << (K - 1)) - 1;
+  if (idx >= lim) return;
+  uint32_t k = 63 - __clzll(idx + 1);
+  uint64_t j = idx + 1 - (1ull << k);
+  table[idx] = top[j << (K - 1 - k)];
+}
+
+// single-thread setup: decide whether `root` is standard or Montgomery, find its order, n^-1 table
+struct domain_probe { int log_order; int was_montgomery; fr_t root_mont; fr_t ninv[33]; };
+__global__ void k_domain_probe(fr_t root, domain_probe* out) {
+  if (blockIdx.x || threadIdx.x) return;
+  fr_t cand[2] = {to_mont(root), root};       // reading 0: bytes are standard form; 1: already Montgomery
+  fr_t minus1 = neg(one<fr_t>());
+  out->log_order = -1;
+  for (int r = 0; r < 2; r++) {
+    fr_t x = cand[r];
+    if (is_zero(x)) continue;
+    // order 2^k  <=>  x^(2^(k-1)) = -1  (k >= 1);  order 1 <=> x = 1
+    if (eq(x, one<fr_t>())) { out->log_order = 0; out->was_montgomery = r; out->root_mont = x; break; }
+    int found = -1;
+    for (int k = 1; k <= 32; k++) {
+      if (eq(x, minus1)) { found = k; break; }
+      x = sqr(x);
+    }
+    if (found >= 0) { out->log_order = found; out->was_montgomery = r; out->root_mont = cand[r]; break; }
+  }
+  fr_t two = add(one<fr_t>(), one<fr_t>());
+  fr_t half = inv(two);
+  fr_t acc = one<fr_t>();
+  for (int k = 0; k <= 32; k++) { out->ninv[k] = acc; acc = mul(acc, half); }
+}
+
+// ------------------------------------------------------------------ domain
+struct CosetTable { fr_t gen; uint32_t n; bool inverse; fr_t* dev; };
+
+struct Domain {
+  bool ready = false;
+  int device = -1;
+  uint32_t K = 0;            // log2 of the root's order
+  fr_t root_mont;            // primitive 2^K-th root, Montgomery
+  fr_t* table = nullptr;     // 2^K - 1 twiddles, stage-major
+  fr_t ninv[33];             // 2^-k, Montgomery
+  std::vector<CosetTable> cosets;
+};
+static Domain g_dom;
+static std::mutex g_dom_mu;
+
+static void release_locked() {
+  if (g_dom.table) cudaFree(g_dom.table);
+  for (auto& c : g_dom.cosets) cudaFree(c.dev);
+  g_dom = Domain();
+}
+
+static int init_domain(const fr_t& root, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_dom_mu);
+  if (g_dom.ready) return B381_SUCCESS;   // ICICLE semantics: repeated init is a no-op until release
+  domain_probe* d_probe;
+  domain_probe h;
+  if (cudaMalloc(&d_probe, sizeof(domain_probe)) != cudaSuccess) return B381_ALLOCATION_FAILED;
+  k_domain_probe<<<1, 1, 0, st>>>(root, d_probe);
+  cudaError_t e = cudaMemcpyAsync(&h, d_probe, sizeof(h), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_probe);
+  if (e != cudaSuccess) return map_cuda_error(e);
+  if (h.log_order < 1 || h.log_order > (int)kMaxDomainLog) return B381_INVALID_ARGUMENT;
+  const uint32_t K = (uint32_t)h.log_order;
+  fr_t* table;
+  const uint64_t entries = (1ull << K) - 1;
+  if (cudaMalloc(&table, entries * sizeof(fr_t)) != cudaSuccess) return B381_OUT_OF_MEMORY;
+  // top level: T[2^(K-1)-1 + j] = root^j, j < 2^(K-1)
+  fr_t* top = table + ((1ull << (K - 1)) - 1);
+  const uint64_t half = 1ull << (K - 1);
+  fr_t one_m = {FR_ONE_INIT};
+  k_fr_powers<<<grid_for((half + 63) / 64, 128), 128, 0, st>>>(h.root_mont, one_m, half, top);
+  if (K > 1) k_twiddle_subsample<<<grid_for(half - 1, 256), 256, 0, st>>>(top, K, table);
+  e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess) e = cudaGetLastError();
+  if (e != cudaSuccess) { cudaFree(table); return map_cuda_error(e); }
+  cudaGetDevice(&g_dom.device);
+  g_dom.K = K;
+  g_dom.root_mont = h.root_mont;
+  g_dom.table = table;
+  memcpy(g_dom.ninv, h.ninv, sizeof(h.ninv));
+  g_dom.ready = true;
+  return B381_SUCCESS;
+}
+
+static bool fr_host_eq(const fr_t& a, const fr_t& b) { return memcmp(&a, &b, sizeof(fr_t)) == 0; }
+static bool fr_host_is_zero(const fr_t& a) { return (a.l[0] | a.l[1] | a.l[2] | a.l[3]) == 0; }
+
+__global__ void k_fr_inv1(fr_t x, fr_t* out) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) *out = inv(x);
+}
+
+// Coset power tables, cached per (generator, log size, direction) -- the reference caches only the
+// first generator it sees (ntt_kernels.cu:1701-1705).  forward: g^i ; inverse: g^-k * 2^-n.
+// Caller holds g_dom_mu.
+static int coset_table(const fr_t& gen, uint32_t n, bool inverse, cudaStream_t st, const fr_t** out) {
+  for (auto& c : g_dom.cosets)
+    if (c.n == n && c.inverse == inverse && fr_host_eq(c.gen, gen)) { *out = c.dev; return B381_SUCCESS; }
+  if (g_dom.cosets.size() >= 8) {          // small FIFO cache; eviction is rare, so a full sync is fine
+    cudaDeviceSynchronize();
+    cudaFree(g_dom.cosets.front().dev);
+    g_dom.cosets.erase(g_dom.cosets.begin());
+  }
+  fr_t* dev;
+  const uint64_t N = 1ull << n;
+  if (cudaMalloc(&dev, N * sizeof(fr_t)) != cudaSuccess) return B381_OUT_OF_MEMORY;
+  fr_t g = gen, base = {FR_ONE_INIT};
+  if (inverse) {
+    base = g_dom.ninv[n];
+    fr_t* d_g;
+    if (cudaMalloc(&d_g, sizeof(fr_t)) != cudaSuccess) { cudaFree(dev); return B381_OUT_OF_MEMORY; }
+    k_fr_inv1<<<1, 1, 0, st>>>(gen, d_g);
+    cudaError_t e = cudaMemcpyAsync(&g, d_g, sizeof(fr_t), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_g);
+    if (e != cudaSuccess) { cudaFree(dev); return map_cuda_error(e); }
+  }
+  k_fr_powers<<<grid_for((N + 63) / 64, 128), 128, 0, st>>>(g, base, N, dev);
+  if (cudaGetLastError() != cudaSuccess) { cudaFree(dev); return B381_UNKNOWN_ERROR; }
+  g_dom.cosets.push_back(CosetTable{gen, n, inverse, dev});
+  *out = dev;
+  return B381_SUCCESS;
+}
+
+// ------------------------------------------------------------------ launcher
+static int ntt_run(const fr_t* input, int size, int dir, const b381_ntt_config* cfg, fr_t* output) {
+  if (!cfg) return B381_INVALID_POINTER;
+  if (size < 0) return B381_INVALID_ARGUMENT;
+  if (size == 0) return B381_SUCCESS;
+  if (!input || !output) return B381_INVALID_POINTER;
+  if (size & (size - 1)) return B381_INVALID_ARGUMENT;       // power of two (ntt_kernels.cu:717-722)
+  uint32_t n = 0;
+  while ((1u << n) < (uint32_t)size) n++;
+  const uint32_t batch = cfg->batch_size > 0 ? (uint32_t)cfg->batch_size : 1u;
+  const uint64_t total = (uint64_t)batch << n;
+  const bool inverse = dir == B381_NTT_INVERSE;
+  cudaStream_t st = (cudaStream_t)cfg->stream;
+
+  std::unique_lock<std::mutex> lk(g_dom_mu);
+  if (!g_dom.ready || n > g_dom.K) return B381_INVALID_ARGUMENT;   // domain missing / too small (:724-731)
+  const fr_t* tw = g_dom.table;
+  fr_t ninv = g_dom.ninv[n];
+  const fr_t one_m = {FR_ONE_INIT};
+  const fr_t* gen = reinterpret_cast<const fr_t*>(&cfg->coset_gen);
+  bool has_coset = !fr_host_eq(*gen, one_m) && !fr_host_is_zero(*gen);
+  const fr_t* ctab = nullptr;
+  if (has_coset) {
+    int rc = coset_table(*gen, n, inverse, st, &ctab);
+    if (rc != B381_SUCCESS) return rc;
+  }
+
+  bool perm_in = false, perm_out = false;
+  switch (cfg->ordering) {
+    case B381_kNN: perm_out = true; break;
+    case B381_kNR: case B381_kNM: break;
+    case B381_kRN: case B381_kMN: perm_in = true; perm_out = true; break;
+    case B381_kRR: perm_in = true; break;
+    default: return B381_INVALID_ARGUMENT;
+  }
+
+  cudaError_t e;
+  {
+    Scratch sc(st);
+    const fr_t* d_in;
+    if ((e = stage_in(sc, input, total, cfg->are_inputs_on_device, &d_in)) != cudaSuccess) return map_cuda_error(e);
+    fr_t* d_out = output;
+    if (!cfg->are_outputs_on_device && (e = sc.alloc(&d_out, total)) != cudaSuccess) return map_cuda_error(e);
+
+    ntt_pass_plan plan[8];
+    const size_t P = (size_t)ntt_plan_passes(n, plan);
+    const bool inplace = (d_in == d_out);
+    fr_t* work = d_out;
+    if (P >= 2 && (perm_in || perm_out) && (inplace || perm_out)) {
+      if ((e = sc.alloc(&work, total)) != cudaSuccess) return map_cuda_error(e);
+    }
+    for (size_t i = 0; i < P; i++) {
+      ntt_pass_params p;
+      memset(&p, 0, sizeof(p));
+      p.n = n; p.lo = plan[i].lo; p.S = plan[i].S; p.g = plan[i].g; p.x = plan[i].x;
+      p.total = total;
+      if (cfg->columns_batch) { p.estride = batch; p.bstride = 1; }
+      else { p.estride = 1; p.bstride = 1ull << n; }
+      p.inverse = inverse;
+      p.twiddles = tw;
+      const bool first = (i == 0), last = (i + 1 == P);
+      p.perm_in = first && perm_in;
+      p.perm_out = last && perm_out;
+      if (first && has_coset && !inverse) p.pre_scale = ctab;
+      if (last && inverse) {
+        if (has_coset) p.post_scale = ctab;          // g^-k * 2^-n
+        else { p.post_const = ninv; p.has_post_const = 1; }
+      }
+      const fr_t* src = first ? d_in : work;
+      fr_t* dst = last ? d_out : work;
+      const uint32_t tile_log = p.S + p.g + p.x;
+      const uint64_t tiles = (total + (1ull << tile_log) - 1) >> tile_log;
+      const size_t smem = (size_t)2 * sizeof(uint4) << tile_log;
+      static bool attr_set = false;
+      if (!attr_set) {
+        cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(uint4) * kTile);
+        attr_set = true;
+      }
+      k_ntt_pass<<<(unsigned)tiles, kNttThreads, smem, st>>>(p, src, dst);
+    }
+    lk.unlock();   // tables stay valid: release_domain synchronises the device before freeing
+    if ((e = cudaGetLastError()) != cudaSuccess) return map_cuda_error(e);
+    if (!cfg->are_outputs_on_device) {
+      e = cudaMemcpyAsync(output, d_out, total * sizeof(fr_t), cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return map_cuda_error(e);
+    }
+  }
+  if (!cfg->is_async) {
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) return map_cuda_error(e);
+  }
+  return B381_SUCCESS;
+}
+
+}  // namespace b381
+using namespace b381;
+
+extern "C" {
+int b381_ntt_init_domain(const b381_fr* root, const b381_ntt_init_domain_config* cfg) {
+  if (!root) return B381_INVALID_POINTER;
+  cudaStream_t st = cfg ? (cudaStream_t)cfg->stream : 0;
+  return init_domain(*reinterpret_cast<const fr_t*>(root), st);
+}
+int b381_ntt_release_domain(void) {
+  std::lock_guard<std::mutex> lk(g_dom_mu);
+  cudaDeviceSynchronize();
+  release_locked();
+  return B381_SUCCESS;
+}
+int b381_ntt(const b381_fr* in, int size, int dir, const b381_ntt_config* cfg, b381_fr* out) {
+  return ntt_run((const fr_t*)in, size, dir, cfg, (fr_t*)out);
+}
+int b381_ntt_get_rou_from_domain(uint64_t logn, b381_fr* rou) {
+  if (!rou) return B381_INVALID_POINTER;
+  std::lock_guard<std::mutex> lk(g_dom_mu);
+  if (!g_dom.ready || logn > g_dom.K) return B381_INVALID_ARGUMENT;
+  fr_t v;
+  if (logn == 0) {
+    v = fr_t{FR_ONE_INIT};
+  } else if (logn == 1) {
+    // omega_2 = -1 = r - R in Montgomery form
+    const uint64_t m[4] = FR_MODULUS_INIT, o[4] = FR_ONE_INIT;
+    uint64_t br = 0;
+    for (int i = 0; i < 4; i++) {
+      unsigned __int128 d = (unsigned __int128)m[i] - o[i] - br;
+      v.l[i] = (uint64_t)d;
+      br = (uint64_t)(d >> 64) & 1;
+    }
+  } else {
+    // omega_{2^logn} = T_{logn-1}[1]
+    cudaError_t e = cudaMemcpy(&v, g_dom.table + ((1ull << (logn - 1)) - 1) + 1, sizeof(fr_t), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return map_cuda_error(e);
+  }
+  memcpy(rou, &v, sizeof(v));
+  return B381_SUCCESS;
+}
+b381_ntt_config b381_default_ntt_config(void) {
+  b381_ntt_config c;
+  memset(&c, 0, sizeof(c));
+  const uint64_t o[4] = FR_ONE_INIT;
+  memcpy(&c.coset_gen, o, sizeof(o));
+  c.batch_size = 1;
+  c.ordering = B381_kNN;
+  return c;
+}
+// reference-named flat API
+int bls12_381_ntt_cuda(const b381_fr* in, int size, int dir, const b381_ntt_config* cfg, b381_fr* out) { return b381_ntt(in, size, dir, cfg, out); }
+int bls12_381_field_ntt_cuda(const b381_fr* in, int size, int dir, const b381_ntt_config* cfg, b381_fr* out) { return b381_ntt(in, size, dir, cfg, out); }
+int bls12_381_ntt_init_domain_cuda(const b381_fr* r, const b381_ntt_init_domain_config* c) { return b381_ntt_init_domain(r, c); }
+int bls12_381_field_ntt_init_domain_cuda(const b381_fr* r, const b381_ntt_init_domain_config* c) { return b381_ntt_init_domain(r, c); }
+int bls12_381_ntt_release_domain_cuda(void) { return b381_ntt_release_domain(); }
+int bls12_381_field_ntt_release_domain_cuda(void) { return b381_ntt_release_domain(); }
+int bls12_381_coset_ntt_cuda(const b381_fr* in, int size, int dir, const b381_fr* coset_gen, const b381_ntt_config* cfg, b381_fr* out) {
+  if (!cfg || !coset_gen) return B381_INVALID_POINTER;
+  b381_ntt_config c = *cfg;
+  c.coset_gen = *coset_gen;
+  return b381_ntt(in, size, dir, &c, out);
+}
+}

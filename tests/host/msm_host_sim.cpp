@@ -1,8 +1,9 @@
 // CPU-only driver for the per-thread MSM bodies in csrc/msm_core.cuh (TEST INFRASTRUCTURE).
 // Runs exactly the kernel pipeline of csrc/msm.cu with a serial loop per "kernel" and
 // std::stable_sort in place of the device radix sort.  Usage:
-//   msm_host_sim <g1|g2> <n> <c> <K> <L> <scalars_mont 0|1> <infile> ; prints result hex (std form)
+//   msm_host_sim <g1|g2> <n> <c> <K> <L> <scalars_mont 0|1> <infile> [factor]; prints result hex (std form)
 // infile = n*32 B scalars followed by n*(96|192) B Montgomery affine points.
+// With factor > 1 the bases are first expanded exactly like k_precompute_bases does.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -13,13 +14,24 @@
 using namespace b381;
 
 template <class F>
-int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f) {
+int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint32_t factor) {
   std::vector<fr_t> sc(n);
   std::vector<affine_t<F>> pts(n);
   if (fread(sc.data(), sizeof(fr_t), n, f) != n) return 2;
   if (fread(pts.data(), sizeof(affine_t<F>), n, f) != n) return 2;
-  msm_shape sh;
-  sh.n = n; sh.c = c; sh.W = (256 + c - 1) / c; sh.B = 1u << (c - 1); sh.nbuckets = sh.W * sh.B;
+  msm_shape sh = make_msm_shape(n, c, 255, factor);
+  if (factor > 1) {
+    std::vector<affine_t<F>> ex((size_t)n * factor);
+    for (uint32_t i = 0; i < n; i++) {
+      ex[i] = pts[i];
+      xyzz_t<F> acc = to_xyzz(pts[i]);
+      for (uint32_t k = 1; k < factor; k++) {
+        for (uint32_t b = 0; b < c * sh.Wf; b++) acc = xyzz_dbl(acc);
+        ex[(size_t)k * n + i] = xyzz_to_affine(acc);
+      }
+    }
+    pts.swap(ex);
+  }
   size_t total = (size_t)n * sh.W;
   std::vector<uint32_t> keys(total), vals(total);
   for (uint32_t i = 0; i < n; i++) msm_digits_body(i, sc.data(), mont, sh, keys.data(), vals.data());
@@ -41,11 +53,11 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f) {
   for (uint32_t b = 0; b < sh.nbuckets; b++) msm_finalize_body<F>(b, sh.nbuckets, tstart.data(), counts.data(), partial.data(), buckets.data());
   if (L > sh.B) L = sh.B;
   uint32_t segs = sh.B / L;
-  std::vector<xyzz_t<F>> seg(sh.W * segs);
-  for (uint32_t g = 0; g < sh.W * segs; g++) msm_segment_body<F>(g, sh.W, sh.B, L, buckets.data(), seg.data());
+  std::vector<xyzz_t<F>> seg(sh.Wf * segs);
+  for (uint32_t g = 0; g < sh.Wf * segs; g++) msm_segment_body<F>(g, sh.Wf, sh.B, L, buckets.data(), seg.data());
   for (uint32_t half = segs / 2; half >= 1; half /= 2)
-    for (uint32_t g = 0; g < sh.W * half; g++) msm_tree_body<F>(g, sh.W, segs, half, seg.data());
-  xyzz_t<F> r = msm_combine<F>(seg.data(), segs, sh.W, sh.c);
+    for (uint32_t g = 0; g < sh.Wf * half; g++) msm_tree_body<F>(g, sh.Wf, segs, half, seg.data());
+  xyzz_t<F> r = msm_combine<F>(seg.data(), segs, sh.Wf, sh.c);
   jacobian_t<F> o = msm_result_encode<F>(r, false);
   const unsigned char* p = (const unsigned char*)&o;
   for (size_t i = 0; i < sizeof(o); i++) printf("%02x", p[i]);
@@ -60,7 +72,8 @@ int main(int argc, char** argv) {
   bool mont = atoi(argv[6]) != 0;
   FILE* f = fopen(argv[7], "rb");
   if (!f) return 3;
-  int rc = g2 ? run<fq2_t>(n, c, K, L, mont, f) : run<fq_t>(n, c, K, L, mont, f);
+  uint32_t factor = argc > 8 ? atoi(argv[8]) : 1;
+  int rc = g2 ? run<fq2_t>(n, c, K, L, mont, f, factor) : run<fq_t>(n, c, K, L, mont, f, factor);
   fclose(f);
   return rc;
 }

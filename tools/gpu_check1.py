@@ -1,0 +1,203 @@
+#!/usr/bin/env python3
+"""First GPU bring-up: probes, vecops, G1/G2 MSM correctness + timing sweep (dev tool, not a test)."""
+import ctypes as C
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from midnight_bls12_381_cuda_b200 import _lib as L
+from oracle import pyref as P
+
+lib = L.lib()
+print(lib.b381_version().decode(), torch.cuda.get_device_name(0))
+
+
+def probes():
+    ms = C.c_float()
+    v = C.c_double()
+    for it in (2000, 8000):
+        L.check(lib.b381_bench_imad_peak(it, C.byref(v), C.byref(ms)), "imad")
+        print(f"imad.wide peak: {v.value:.4e} MAD/s  ({ms.value:.3f} ms)")
+    for f, name in ((0, "fq"), (1, "fr")):
+        L.check(lib.b381_bench_field_mul(f, 2000, C.byref(v), C.byref(ms)), "mul")
+        print(f"{name} mul: {v.value:.4e} mul/s ({ms.value:.3f} ms)")
+
+
+def fr_arr(vals):
+    a = np.zeros((len(vals), 4), dtype=np.uint64)
+    for i, v in enumerate(vals):
+        a[i] = P.to_limbs(v, 4)
+    return a
+
+
+def vecops():
+    rng = P.SplitMix64(7)
+    n = 1000
+    a = [rng.fr() for _ in range(n)]
+    b = [rng.fr() for _ in range(n)]
+    a[0], b[0] = 0, 0
+    a[1], b[1] = P.R_MOD - 1, P.R_MOD - 1
+    da = torch.from_numpy(fr_arr([P.fr_to_mont(x) for x in a]).view(np.int64)).cuda()
+    db = torch.from_numpy(fr_arr([P.fr_to_mont(x) for x in b]).view(np.int64)).cuda()
+    out = torch.empty_like(da)
+    cfg = lib.b381_default_vecops_config()
+    cfg.is_a_on_device = cfg.is_b_on_device = cfg.is_result_on_device = True
+    for name, fn, ref in (("add", lib.b381_vector_add, lambda x, y: (x + y) % P.R_MOD),
+                          ("sub", lib.b381_vector_sub, lambda x, y: (x - y) % P.R_MOD),
+                          ("mul", lib.b381_vector_mul, lambda x, y: (x * y) % P.R_MOD)):
+        L.check(fn(L.ptr(da), L.ptr(db), C.c_uint64(n), C.byref(cfg), L.ptr(out)), name)
+        got = out.cpu().numpy().view(np.uint64)
+        exp = fr_arr([P.fr_to_mont(ref(x, y)) for x, y in zip(a, b)])
+        assert (got == exp).all(), name
+        print("vecop", name, "ok")
+
+
+def g1_pool(m, seed=11):
+    rng = P.SplitMix64(seed)
+    k0, d = rng.fr(), rng.fr()
+    D = P.g1_mul(d, P.G1_GEN)
+    pts, ks = [], []
+    cur, k = P.g1_mul(k0, P.G1_GEN), k0
+    for _ in range(m):
+        pts.append(cur)
+        ks.append(k)
+        cur = P.g1_add(cur, D)
+        k = (k + d) % P.R_MOD
+    return pts, ks
+
+
+def g2_pool(m, seed=13):
+    rng = P.SplitMix64(seed)
+    k0, d = rng.fr(), rng.fr()
+    D = P.g2_mul(d, P.G2_GEN)
+    pts, ks = [], []
+    cur, k = P.g2_mul(k0, P.G2_GEN), k0
+    for _ in range(m):
+        pts.append(cur)
+        ks.append(k)
+        cur = P.g2_add(cur, D)
+        k = (k + d) % P.R_MOD
+    return pts, ks
+
+
+def rand_scalars_np(n, seed):
+    g = np.random.default_rng(seed)
+    a = g.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + g.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    a[:, 3] &= np.uint64((1 << 62) - 1)     # < 2^254 < r : canonical
+    return a
+
+
+def class_sums(sc, m):
+    """sum of scalars per residue class i mod m, as python ints."""
+    n = sc.shape[0]
+    lo = (sc & np.uint64(0xFFFFFFFF)).reshape(n // m, m, 4).sum(axis=0)
+    hi = (sc >> np.uint64(32)).reshape(n // m, m, 4).sum(axis=0)
+    out = []
+    for j in range(m):
+        v = 0
+        for l in range(4):
+            v += (int(lo[j, l]) + (int(hi[j, l]) << 32)) << (64 * l)
+        out.append(v)
+    return out
+
+
+def run_msm(group, sc_np, bases_dev, n, c=0, mont=False, factor=1):
+    cfg = lib.b381_default_msm_config()
+    cfg.c = c
+    cfg.precompute_factor = factor
+    cfg.are_scalars_on_device = True
+    cfg.are_points_on_device = True
+    cfg.are_scalars_montgomery_form = mont
+    cfg.are_points_montgomery_form = True
+    d_sc = torch.from_numpy(sc_np.view(np.int64)).cuda()
+    res = np.zeros(144 if group == "g1" else 288, dtype=np.uint8)
+    fn = lib.b381_g1_msm if group == "g1" else lib.b381_g2_msm
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    L.check(fn(L.ptr(d_sc), L.ptr(bases_dev), n, C.byref(cfg), L.ptr(res)), "msm")
+    dt = time.perf_counter() - t0
+    return res.tobytes(), dt
+
+
+def timings():
+    buf = (C.c_float * 8)()
+    k = lib.b381_msm_last_timings(buf, 8)
+    return [round(buf[i], 3) for i in range(k)]
+
+
+def msm_small():
+    pts, ks = g1_pool(300)
+    pb = b"".join(P.g1_affine_mont_bytes(p) for p in pts)
+    dev = torch.frombuffer(bytearray(pb), dtype=torch.uint8).cuda()
+    rng = P.SplitMix64(5)
+    for n in (1, 2, 8, 33, 300):
+        sc = [rng.fr() for _ in range(n)]
+        if n > 4:
+            sc[0], sc[1], sc[2] = 0, 1, P.R_MOD - 1
+        exp = P.g1_result_std_bytes(P.g1_mul(sum(s * k for s, k in zip(sc, ks)) % P.R_MOD, P.G1_GEN))
+        for c in (0, 4, 9):
+            got, _ = run_msm("g1", fr_arr(sc), dev, n, c=c)
+            assert got == exp, ("g1", n, c)
+            got, _ = run_msm("g1", fr_arr([P.fr_to_mont(s) for s in sc]), dev, n, c=c, mont=True)
+            assert got == exp, ("g1 mont", n, c)
+        print("g1 msm ok n =", n)
+    # all-identical bases (doubling path) + 1..n scalars: sum i*G = n(n+1)/2 G   (core/msm.rs:1681-1694)
+    n = 64
+    dev1 = torch.frombuffer(bytearray(P.g1_affine_mont_bytes(P.G1_GEN) * n), dtype=torch.uint8).cuda()
+    got, _ = run_msm("g1", fr_arr(list(range(1, n + 1))), dev1, n)
+    assert got == P.g1_result_std_bytes(P.g1_mul(2080, P.G1_GEN))
+    got, _ = run_msm("g1", fr_arr([0] * n), dev1, n)
+    assert got == P.g1_result_std_bytes(None)
+    print("g1 identical-bases / zero ok")
+    pts2, ks2 = g2_pool(40)
+    dev2 = torch.frombuffer(bytearray(b"".join(P.g2_affine_mont_bytes(p) for p in pts2)), dtype=torch.uint8).cuda()
+    for n in (1, 7, 40):
+        sc = [rng.fr() for _ in range(n)]
+        exp = P.g2_result_std_bytes(P.g2_mul(sum(s * k for s, k in zip(sc, ks2)) % P.R_MOD, P.G2_GEN))
+        got, _ = run_msm("g2", fr_arr(sc), dev2, n)
+        assert got == exp, ("g2", n)
+        print("g2 msm ok n =", n)
+
+
+def msm_large(sizes, cs_by_n):
+    m = 4096
+    pts, ks = g1_pool(m, seed=21)
+    pool = np.frombuffer(b"".join(P.g1_affine_mont_bytes(p) for p in pts), dtype=np.uint8).reshape(m, 96)
+    os.environ["B381_MSM_TIMING"] = "1"
+    for logn in sizes:
+        n = 1 << logn
+        dev = torch.from_numpy(np.tile(pool, (n // m, 1))).cuda()
+        sc = rand_scalars_np(n, logn)
+        sums = class_sums(sc, m)
+        exp = P.g1_result_std_bytes(P.g1_mul(sum(s * k for s, k in zip(sums, ks)) % P.R_MOD, P.G1_GEN))
+        for c in cs_by_n.get(logn, [0]):
+            got, dt = run_msm("g1", sc, dev, n, c=c)
+            got, dt = run_msm("g1", sc, dev, n, c=c)
+            ok = got == exp
+            print(f"g1 msm 2^{logn} c={c}: {'OK' if ok else 'MISMATCH'} wall {dt*1e3:.2f} ms  phases(ms) {timings()}  -> {n/dt:.3e} pts/s", flush=True)
+        del dev
+    # G2
+    m2 = 256
+    pts2, ks2 = g2_pool(m2, seed=23)
+    pool2 = np.frombuffer(b"".join(P.g2_affine_mont_bytes(p) for p in pts2), dtype=np.uint8).reshape(m2, 192)
+    for logn in (12, 16):
+        n = 1 << logn
+        dev = torch.from_numpy(np.tile(pool2, (n // m2, 1))).cuda()
+        sc = rand_scalars_np(n, 100 + logn)
+        sums = class_sums(sc, m2)
+        exp = P.g2_result_std_bytes(P.g2_mul(sum(s * k for s, k in zip(sums, ks2)) % P.R_MOD, P.G2_GEN))
+        got, dt = run_msm("g2", sc, dev, n)
+        got, dt = run_msm("g2", sc, dev, n)
+        print(f"g2 msm 2^{logn}: {'OK' if got == exp else 'MISMATCH'} wall {dt*1e3:.2f} ms phases {timings()}", flush=True)
+
+
+if __name__ == "__main__":
+    probes()
+    vecops()
+    msm_small()
+    msm_large([12, 16, 20, 22, 24], {20: [0, 13, 15, 16], 22: [0, 16, 18], 24: [0, 16, 18, 20]})
+    print("ALL DONE")
