@@ -1,0 +1,185 @@
+"""G1/G2 MSM parity on the GPU, through the C ABI (via the core/msm.rs-shaped Python layer):
+golden vectors, oracle.c on the same seeded inputs, edge cases of the reference's tests
+(test_msm_security.cu:908-941, core/msm.rs:1653-2111) and size-independent checks at full size."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyref as P
+from vectors import fr_array, fr_ints, load_golden, msm_case_inputs
+
+pytestmark = pytest.mark.gpu
+GOLD = load_golden()
+
+
+def mont(sc_int_arr):
+    return fr_array([P.fr_to_mont(v) for v in fr_ints(sc_int_arr)])
+
+
+def raw_msm(b381, group, scalars, bases, n, **kw):
+    """direct C-ABI call with explicit flags; host buffers unless told otherwise."""
+    lib = b381.lib()
+    cfg = lib.b381_default_msm_config()
+    cfg.are_points_montgomery_form = kw.get("points_mont", True)
+    cfg.are_scalars_montgomery_form = kw.get("scalars_mont", False)
+    cfg.c = kw.get("c", 0)
+    cfg.bitsize = kw.get("bitsize", 0)
+    cfg.batch_size = kw.get("batch", 1)
+    cfg.are_points_shared_in_batch = kw.get("shared", True)
+    cfg.precompute_factor = kw.get("factor", 1)
+    cfg.are_scalars_on_device = kw.get("scalars_on_device", False)
+    cfg.are_points_on_device = kw.get("points_on_device", False)
+    k = 1 if group == "g1" else 2
+    res = np.zeros((cfg.batch_size, 18 * k), dtype=np.uint64)
+    fn = lib.b381_g1_msm if k == 1 else lib.b381_g2_msm
+    code = fn(b381.ptr(scalars), b381.ptr(bases), n, C.byref(cfg), b381.ptr(res))
+    assert code == 0, b381.ERROR_NAMES.get(code, code)
+    return res
+
+
+@pytest.mark.parametrize("case", GOLD["g1_msm"], ids=[c["name"] for c in GOLD["g1_msm"]])
+def test_g1_golden(cuda, b381, case):
+    sc, bases = msm_case_inputs(case, "g1")
+    n = case["n"]
+    assert raw_msm(b381, "g1", sc, bases, n).tobytes().hex() == case["result"]
+    assert raw_msm(b381, "g1", mont(sc), bases, n, scalars_mont=True, c=7).tobytes().hex() == case["result"]
+    # the reference's own flat test entry point: Jacobian Montgomery result (icicle_curve_api.cu:679-706)
+    lib = b381.lib()
+    cfg = lib.b381_default_msm_config()
+    res = np.zeros(18, dtype=np.uint64)
+    assert lib.bls12_381_g1_msm_cuda(b381.ptr(sc), b381.ptr(bases), n, C.byref(cfg), b381.ptr(res)) == 0
+    z = P.from_limbs(res[12:18])
+    exp = bytes.fromhex(case["result"])
+    if z == 0:
+        assert exp[96:] == bytes(48)
+    else:
+        assert z == P.FQ_R
+        assert P.fq_from_mont(P.from_limbs(res[0:6])).to_bytes(48, "little") == exp[:48]
+        assert P.fq_from_mont(P.from_limbs(res[6:12])).to_bytes(48, "little") == exp[48:96]
+
+
+@pytest.mark.parametrize("case", GOLD["g2_msm"], ids=[c["name"] for c in GOLD["g2_msm"]])
+def test_g2_golden(cuda, b381, case):
+    sc, bases = msm_case_inputs(case, "g2")
+    assert raw_msm(b381, "g2", sc, bases, case["n"]).tobytes().hex() == case["result"]
+    assert raw_msm(b381, "g2", mont(sc), bases, case["n"], scalars_mont=True, c=5).tobytes().hex() == case["result"]
+
+
+@pytest.mark.parametrize("logn,seed", [(10, 1), (14, 2), (16, 0xB12381_0016)])
+def test_g1_vs_oracle_random(cuda, b381, oracle, logn, seed):
+    """config 1 of BASELINE.json: random points/scalars, CPU path vs new kernel, bit-exact."""
+    n = 1 << logn
+    rng = P.SplitMix64(seed)
+    k0, d = rng.fr(), rng.fr()
+    bases = oracle.gen_series(1, P.to_limbs(k0, 4), P.to_limbs(d, 4), n)
+    sc = oracle.random_fr(seed + 1000, n)
+    exp = oracle.msm(1, sc, bases)
+    assert raw_msm(b381, "g1", sc, bases, n).tobytes() == exp.tobytes()
+    # through the core/msm.rs-shaped API with device-resident bases and Montgomery scalars
+    import midnight_bls12_381_cuda_b200 as M
+    ctx = M.GpuMsmContext()
+    dev = ctx.upload_g1_bases(bases)
+    got = ctx.msm_with_device_bases(mont(sc), dev)
+    x, y = got
+    assert x.to_bytes(48, "little") + y.to_bytes(48, "little") == exp.tobytes()[:96]
+    assert ctx.msm_with_device_bases_async(mont(sc), dev).wait() == got
+
+
+def test_g2_vs_oracle_random(cuda, b381, oracle):
+    n = 1 << 10
+    rng = P.SplitMix64(404)
+    k0, d = rng.fr(), rng.fr()
+    bases = oracle.gen_series(2, P.to_limbs(k0, 4), P.to_limbs(d, 4), n)
+    sc = oracle.random_fr(405, n)
+    assert raw_msm(b381, "g2", sc, bases, n).tobytes() == oracle.msm(2, sc, bases).tobytes()
+
+
+def test_edge_cases(cuda, b381, oracle):
+    g = oracle.generator(1)
+    inf = np.zeros(12, dtype=np.uint64)
+    # n = 0 -> identity (test_msm_security.cu "empty"), results (0,1,0)
+    assert raw_msm(b381, "g1", fr_array([]), np.zeros((0, 12), dtype=np.uint64), 0).tobytes() == P.g1_result_std_bytes(None)
+    # all-zero scalars, infinity bases, mixed zeros
+    n = 300
+    bases = np.tile(g, (n, 1))
+    assert raw_msm(b381, "g1", fr_array([0] * n), bases, n).tobytes() == P.g1_result_std_bytes(None)
+    sc = fr_array([i % 2 for i in range(n)])
+    assert raw_msm(b381, "g1", sc, bases, n).tobytes() == P.g1_result_std_bytes(P.g1_mul(n // 2, P.G1_GEN))
+    bases2 = bases.copy()
+    bases2[::3] = inf
+    exp = sum(i + 1 for i in range(n) if i % 3) % P.R_MOD
+    assert raw_msm(b381, "g1", fr_array(list(range(1, n + 1))), bases2, n).tobytes() == P.g1_result_std_bytes(P.g1_mul(exp, P.G1_GEN))
+    # P and -P with equal scalars cancel inside one bucket
+    neg = np.frombuffer(P.g1_affine_mont_bytes(P.g1_neg(P.G1_GEN)), dtype=np.uint64)
+    pair = np.stack([g, neg] * 8)
+    assert raw_msm(b381, "g1", fr_array([12345] * 16), pair, 16).tobytes() == P.g1_result_std_bytes(None)
+    # r-1 scalars, maximal digits in every window
+    assert raw_msm(b381, "g1", fr_array([P.R_MOD - 1] * 5), np.tile(g, (5, 1)), 5).tobytes() == \
+        P.g1_result_std_bytes(P.g1_mul(5 * (P.R_MOD - 1), P.G1_GEN))
+    # standard-form (non-Montgomery) points are converted on a private copy
+    std = np.frombuffer(P.fq_bytes(P.G1_X) + P.fq_bytes(P.G1_Y), dtype=np.uint64)
+    assert raw_msm(b381, "g1", fr_array([7]), std.reshape(1, 12), 1, points_mont=False).tobytes() == \
+        P.g1_result_std_bytes(P.g1_mul(7, P.G1_GEN))
+    # invalid arguments come back as error codes, never exceptions across the ABI
+    lib = b381.lib()
+    cfg = lib.b381_default_msm_config()
+    assert lib.b381_g1_msm(None, None, 4, C.byref(cfg), b381.ptr(np.zeros(18, dtype=np.uint64))) == 3   # INVALID_POINTER
+    assert lib.b381_g1_msm(b381.ptr(sc), b381.ptr(bases), -1, C.byref(cfg), b381.ptr(np.zeros(18, dtype=np.uint64))) == 11
+
+
+def test_window_sizes_agree(cuda, b381, oracle):
+    """the reference never compares window sizes; we do."""
+    n = 4096
+    bases = oracle.gen_series(1, [3, 0, 0, 0], [5, 0, 0, 0], n)
+    sc = oracle.random_fr(11, n)
+    exp = oracle.msm(1, sc, bases).tobytes()
+    for c in (2, 5, 9, 12, 13, 16):
+        assert raw_msm(b381, "g1", sc, bases, n, c=c).tobytes() == exp, c
+
+
+def test_batch_and_precompute(cuda, b381, oracle):
+    """batch == individual, precompute == standard (core/msm.rs:1980-2111)."""
+    n, b = 2048, 3
+    bases = oracle.gen_series(1, [9, 0, 0, 0], [11, 0, 0, 0], n)
+    sc = oracle.random_fr(21, n * b)
+    singles = [oracle.msm(1, sc[i * n:(i + 1) * n], bases).tobytes() for i in range(b)]
+    got = raw_msm(b381, "g1", sc, bases, n, batch=b)
+    assert [got[i].tobytes() for i in range(b)] == singles
+    # per-batch bases
+    bases_b = oracle.gen_series(1, [1, 0, 0, 0], [7, 0, 0, 0], n * b)
+    singles2 = [oracle.msm(1, sc[i * n:(i + 1) * n], bases_b[i * n:(i + 1) * n]).tobytes() for i in range(b)]
+    got2 = raw_msm(b381, "g1", sc, bases_b, n, batch=b, shared=False)
+    assert [got2[i].tobytes() for i in range(b)] == singles2
+    import midnight_bls12_381_cuda_b200 as M
+    ctx = M.GpuMsmContext()
+    dev = ctx.upload_g1_bases(bases)
+    res = ctx.msm_batch_with_device_bases([mont(sc[i * n:(i + 1) * n]) for i in range(b)], dev)
+    for r, s in zip(res, singles):
+        assert r[0].to_bytes(48, "little") + r[1].to_bytes(48, "little") == s[:96]
+    assert ctx.msm_batch_with_device_bases_async([mont(sc[i * n:(i + 1) * n]) for i in range(b)], dev).wait() == res
+    for factor in (2, 4):
+        pre = ctx.precompute_bases(dev, factor)
+        assert pre.buffer_size() == n * factor and pre.is_precomputed()
+        r = ctx.msm_with_device_bases(mont(sc[:n]), pre)
+        assert r[0].to_bytes(48, "little") + r[1].to_bytes(48, "little") == singles[0][:96]
+
+
+def test_full_size_discrete_log_check(cuda, b381, oracle):
+    """2^20 G1 and 2^16 G2 through the size-independent identity
+    sum s_i (k_i G) = (sum s_i k_i mod r) G with P_i = (k0 + i d) G."""
+    import torch
+    for group, k, logn in (("g1", 1, 20), ("g2", 2, 16)):
+        n = 1 << logn
+        rng = P.SplitMix64(0xB12381_1016 + k)
+        k0, d = rng.fr(), rng.fr()
+        bases = oracle.gen_series(k, P.to_limbs(k0, 4), P.to_limbs(d, 4), n)
+        sc = oracle.random_fr(0xB12381_0016 + k, n)
+        # sum s_i (k0 + i d) = k0 * S0 + d * S1
+        s = fr_ints(sc)
+        dl = (k0 * sum(s) + d * sum(i * v for i, v in enumerate(s))) % P.R_MOD
+        exp = P.g1_result_std_bytes(P.g1_mul(dl, P.G1_GEN)) if k == 1 else P.g2_result_std_bytes(P.g2_mul(dl, P.G2_GEN))
+        d_bases = torch.from_numpy(bases.view(np.int64)).cuda()
+        d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+        got = raw_msm(b381, group, d_sc, d_bases, n, scalars_on_device=True, points_on_device=True)
+        assert got.tobytes() == exp, group

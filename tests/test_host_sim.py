@@ -1,0 +1,121 @@
+"""CPU-only execution of the per-thread bodies that the CUDA kernels are made of
+(csrc/msm_core.cuh, csrc/ntt_core.cuh, csrc/curve.cuh) via tests/host/*_host_sim.cpp, checked
+against the big-integer oracle.  This is how kernel LOGIC is covered where no GPU exists; the
+inline-PTX arithmetic underneath is covered by test_gen_field.py and, on the GPU, by -m gpu."""
+import itertools
+import os
+import subprocess
+
+import pytest
+
+from oracle import pyref as P
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "midnight_bls12_381_cuda_b200", "csrc")
+HOST = os.path.join(ROOT, "tests", "host")
+
+
+@pytest.fixture(scope="module")
+def sims(tmp_path_factory):
+    out = tmp_path_factory.mktemp("hostsim")
+    bins = {}
+    for name in ("msm_host_sim", "ntt_host_sim"):
+        exe = str(out / name)
+        subprocess.run(["g++", "-O2", "-std=c++17", f"-I{HOST}", f"-I{CSRC}", "-o", exe,
+                        os.path.join(HOST, name + ".cpp")], check=True)
+        bins[name] = exe
+    bins["dir"] = str(out)
+    return bins
+
+
+def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1):
+    path = os.path.join(sims["dir"], "msm_in.bin")
+    with open(path, "wb") as f:
+        for s in scalars:
+            f.write(P.fr_bytes(P.fr_to_mont(s) if mont else s))
+        for pt in pts:
+            f.write(P.g1_affine_mont_bytes(pt) if group == "g1" else P.g2_affine_mont_bytes(pt))
+    r = subprocess.run([sims["msm_host_sim"], group, str(len(scalars)), str(c), str(K), str(L), str(int(mont)), path,
+                        str(factor)], capture_output=True, text=True, check=True)
+    return bytes.fromhex(r.stdout.strip())
+
+
+def test_msm_pipeline_g1(sims):
+    rng = P.SplitMix64(42)
+    for (n, c, K, L) in [(1, 4, 2, 2), (8, 4, 2, 4), (33, 5, 3, 4), (64, 8, 16, 16), (150, 7, 4, 8)]:
+        ks = [rng.fr() for _ in range(n)]
+        pts = [P.g1_mul(k, P.G1_GEN) for k in ks]
+        sc = [rng.fr() for _ in range(n)]
+        if n > 4:
+            sc[1], sc[2], sc[3], pts[4] = 0, 1, P.R_MOD - 1, None
+        exp = P.g1_mul(sum(s * k for s, k, p in zip(sc, ks, pts) if p is not None) % P.R_MOD, P.G1_GEN)
+        assert run_msm(sims, "g1", sc, pts, c, K, L) == P.g1_result_std_bytes(exp), (n, c)
+
+
+def test_msm_pipeline_exceptional_cases(sims):
+    # identical bases force the doubling branch of the mixed addition (benches/gpu_msm.rs:30-32)
+    assert run_msm(sims, "g1", [5] * 40, [P.G1_GEN] * 40, 4, 3, 2) == P.g1_result_std_bytes(P.g1_mul(200, P.G1_GEN))
+    # P + (-P) inside one bucket
+    pts = [P.G1_GEN, P.g1_neg(P.G1_GEN)] * 10
+    assert run_msm(sims, "g1", [7] * 20, pts, 4, 3, 2) == P.g1_result_std_bytes(None)
+    # sum i*G = 2080 G with integer-form scalars (core/msm.rs:1681-1694)
+    assert run_msm(sims, "g1", list(range(1, 65)), [P.G1_GEN] * 64, 6, 4, 4, mont=False) == \
+        P.g1_result_std_bytes(P.g1_mul(2080, P.G1_GEN))
+
+
+def test_msm_pipeline_g2_and_precompute(sims):
+    rng = P.SplitMix64(43)
+    n = 12
+    ks = [rng.fr() for _ in range(n)]
+    sc = [rng.fr() for _ in range(n)]
+    pts2 = [P.g2_mul(k, P.G2_GEN) for k in ks]
+    dl = sum(s * k for s, k in zip(sc, ks)) % P.R_MOD
+    assert run_msm(sims, "g2", sc, pts2, 5, 3, 4) == P.g2_result_std_bytes(P.g2_mul(dl, P.G2_GEN))
+    pts1 = [P.g1_mul(k, P.G1_GEN) for k in ks]
+    for factor in (2, 5):
+        assert run_msm(sims, "g1", sc, pts1, 6, 4, 4, factor=factor) == P.g1_result_std_bytes(P.g1_mul(dl, P.G1_GEN))
+
+
+ORD = ["NN", "NR", "RN", "RR"]
+
+
+def run_ntt(sims, n, batch, inverse, ordering, columns, g, inplace, vecs):
+    N = 1 << n
+    flat = [0] * (N * batch)
+    for b in range(batch):
+        for i in range(N):
+            flat[(i * batch + b) if columns else (b * N + i)] = vecs[b][i]
+    path = os.path.join(sims["dir"], "ntt_in.bin")
+    with open(path, "wb") as f:
+        f.write(P.fr_bytes(P.fr_to_mont(P.fr_omega(max(n, 1)))))
+        f.write(P.fr_bytes(P.fr_to_mont(g if g else 1)))
+        for v in flat:
+            f.write(P.fr_bytes(P.fr_to_mont(v)))
+    r = subprocess.run([sims["ntt_host_sim"], str(n), str(batch), str(int(inverse)), str(ordering), str(int(columns)),
+                        str(int(bool(g))), str(int(inplace)), path], capture_output=True, text=True, check=True)
+    raw = bytes.fromhex(r.stdout.strip())
+    flat = [P.fr_from_mont(int.from_bytes(raw[32 * i:32 * i + 32], "little")) for i in range(N * batch)]
+    return [[flat[(i * batch + b) if columns else (b * N + i)] for i in range(N)] for b in range(batch)]
+
+
+def expect_ntt(vec, inverse, ordering, g):
+    o = ORD[ordering]
+    nat = P.apply_ordering(vec, o, "in")
+    y = P.coset_ntt(nat, g, inverse) if g else P.ntt(nat, inverse=inverse)
+    return P.apply_ordering(y, o, "out")
+
+
+@pytest.mark.parametrize("n", [0, 1, 3, 6, 11, 12, 13])
+def test_ntt_passes(sims, n):
+    rng = P.SplitMix64(99 + n)
+    for batch, columns in ((1, False), (3, False), (2, True)):
+        if n >= 12 and batch == 3:
+            continue
+        vecs = [[rng.fr() for _ in range(1 << n)] for _ in range(batch)]
+        combos = list(itertools.product((False, True), range(4), (0, 7), (False, True)))
+        if n >= 11:
+            combos = combos[::7]
+        for inverse, ordering, g, inplace in combos:
+            got = run_ntt(sims, n, batch, inverse, ordering, columns, g, inplace, vecs)
+            for b in range(batch):
+                assert got[b] == expect_ntt(vecs[b], inverse, ordering, g), (n, batch, columns, inverse, ordering, g, inplace)
