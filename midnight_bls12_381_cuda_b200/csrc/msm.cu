@@ -397,13 +397,28 @@ int b381_g1_msm(const b381_fr* s, const b381_g1_affine* p, int n, const b381_msm
 int b381_g2_msm(const b381_fr* s, const b381_g2_affine* p, int n, const b381_msm_config* cfg, b381_g2_projective* r) {
   return msm_entry<fq2_t>((const fr_t*)s, (const g2_affine*)p, n, cfg, r, ResultKind::IcicleStd);
 }
+// The reference's flat entry points call msm::msm_cuda directly, which never reads the Montgomery
+// flags: points are taken as Montgomery, scalars as integers (icicle_curve_api.cu:679-706,
+// msm_kernels.cu:603-903).  Same contract here, whatever the flags say.
+static b381_msm_config flat_cfg(const b381_msm_config* cfg) {
+  b381_msm_config c = *cfg;
+  c.are_points_montgomery_form = true;
+  c.are_scalars_montgomery_form = false;
+  c.batch_size = 1;
+  c.precompute_factor = 1;
+  return c;
+}
 int bls12_381_g1_msm_cuda(const b381_fr* s, const b381_g1_affine* p, int n, const b381_msm_config* cfg,
                           b381_g1_projective* r) {
-  return msm_entry<fq_t>((const fr_t*)s, (const g1_affine*)p, n, cfg, r, ResultKind::JacobianMont);
+  if (!cfg) return B381_INVALID_POINTER;
+  b381_msm_config c = flat_cfg(cfg);
+  return msm_entry<fq_t>((const fr_t*)s, (const g1_affine*)p, n, &c, r, ResultKind::JacobianMont);
 }
 int bls12_381_g2_msm_cuda(const b381_fr* s, const b381_g2_affine* p, int n, const b381_msm_config* cfg,
                           b381_g2_projective* r) {
-  return msm_entry<fq2_t>((const fr_t*)s, (const g2_affine*)p, n, cfg, r, ResultKind::JacobianMont);
+  if (!cfg) return B381_INVALID_POINTER;
+  b381_msm_config c = flat_cfg(cfg);
+  return msm_entry<fq2_t>((const fr_t*)s, (const g2_affine*)p, n, &c, r, ResultKind::JacobianMont);
 }
 int b381_g1_msm_partial(const b381_fr* s, const b381_g1_affine* p, int n, const b381_msm_config* cfg, void* out) {
   return msm_entry<fq_t>((const fr_t*)s, (const g1_affine*)p, n, cfg, out, ResultKind::PartialXyzz);
