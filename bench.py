@@ -1,0 +1,362 @@
+#!/usr/bin/env python3
+"""Headline benchmark: G1 MSM 2^24 points/s (+ Fr NTT 2^24 elements/s) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--log-n 24]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One JSON line on rank 0 (contract in the task statement / DESIGN.md "Measurement").
+  * step      = one G1 MSM over 2^24 resident bases with Montgomery scalars (BASELINE.json config 3),
+                strong-scaled by contiguous point ranges at N > 1 (one XYZZ partial per GPU, NCCL
+                all_gather, combine); the NTT 2^24 is timed right after it and reported under "ntt".
+  * value     = points/s with scalars already in HBM;  e2e = same through the public API with HOST
+                (pinned) scalars, H2D inside the timed region, result read back to the host.
+  * roofline  = k_msm_accumulate against the IMAD.WIDE issue peak MEASURED in this run (the path is
+                integer-pipe bound, not HBM/tensor); "ntt.roofline" is the HBM view north_star asks for.
+  * cpu_baseline / --impl reference = the CPU port oracle/oracle.c (BLST / midnight-curves are not in
+    this image: kind "port") on a bounded sample with every host core.
+The oracle is used here ONLY for that CPU leg and for a one-off result check outside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# G1 generator, Montgomery affine (spec constant; same literal as csrc/field_consts.h)
+G1_GEN_MONT = [0x5cb38790fd530c16, 0x7817fc679976fff5, 0x154f95c7143ba1c1, 0xf0ae6acdf3d0e747, 0xedce6ecc21dbf440,
+               0x120177419e0bfb75, 0xbaac93d50ce72271, 0x8c22631a7918fd8e, 0xdd595f13570725ce, 0x51ac582950405194,
+               0x0e1c8c3fad0059c0, 0x0bbc3efc5008a26a]
+R_TOP_LIMB = 0x73EDA753299D7D48
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--log-n", type=int, default=24)
+    ap.add_argument("--cpu-log-n", type=int, default=0, help="log2 size of the CPU sample (0 = auto)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
+
+    def window(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows[-3:]]
+        mhz = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        reasons = set()
+        for r in rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(mhz) if mhz else None,
+                "sm_max_mhz": float(rows[0][1]) if rows and rows[0][1].replace(".", "").isdigit() else None,
+                "power_w_max": max((float(r[2]) for r in rows if r[2].replace(".", "").isdigit()), default=None),
+                "samples": len(rows), "reasons": sorted(reasons)}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+
+# ----------------------------------------------------------------------------- CPU (reference arm / baseline)
+def cpu_leg(log_n: int, steps: int, warmup: int):
+    """oracle.c Pippenger + radix-2 NTT on all host cores; returns dicts for MSM and NTT."""
+    from oracle import cref as O
+    cores = O.num_threads()
+    n = 1 << log_n
+    bases = O.gen_series(1, [3, 0, 0, 0], [5, 0, 0, 0], n)
+    sc = O.random_fr(0xB12381, n)
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.msm(1, sc, bases, scalars_mont=True)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
+    msm_s = statistics.mean(times)
+    ntt_log = min(log_n + 2, 22)
+    a = O.random_fr(7, 1 << ntt_log)
+    t0 = time.perf_counter()
+    O.ntt(a)
+    ntt_s = time.perf_counter() - t0
+    return {"cores": cores, "msm_log_n": log_n, "msm_s": msm_s, "msm_pts_per_s": n / msm_s,
+            "ntt_log_n": ntt_log, "ntt_s": ntt_s, "ntt_elems_per_s": (1 << ntt_log) / ntt_s}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    log_n = args.cpu_log_n or 18
+    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    r = cpu_leg(log_n, steps, warmup)
+    sample = f"G1 MSM 2^{log_n} points (of the 2^{args.log_n} workload), {steps} steps; Fr NTT 2^{r['ntt_log_n']}"
+    line = {
+        "impl": "reference", "metric": f"g1_msm_2^{args.log_n}_points_per_s", "value": r["msm_pts_per_s"], "unit": "points/s",
+        "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["msm_s"] * 1e3, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64 (6x64 Fq / 4x64 Fr Montgomery)", "data": "synthetic",
+        "config": {"workload": f"G1 MSM, CPU port of the reference's MIDNIGHT_DEVICE=cpu path (Pippenger, OpenMP), sample 2^{log_n}",
+                   "note": "BLST/midnight-curves are absent from this image (SURVEY.md 8c): oracle/oracle.c stands in"},
+        "cpu_baseline": {"value": r["msm_pts_per_s"], "unit": "points/s", "cores": r["cores"], "kind": "port", "sample": sample},
+        "e2e": {"value": r["msm_pts_per_s"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "ntt": {"metric": f"fr_ntt_elems_per_s", "value": r["ntt_elems_per_s"], "unit": "elements/s", "log_n": r["ntt_log_n"]},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import midnight_bls12_381_cuda_b200 as M
+    from midnight_bls12_381_cuda_b200 import _lib as L
+    from midnight_bls12_381_cuda_b200 import dist as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the backend has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    M.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    lib = L.lib()
+    os.environ["B381_MSM_TIMING"] = "1"
+    n = 1 << args.log_n
+    beg, end = D.shard_range(n, rank, world)
+    n_loc = end - beg
+
+    # ---- inputs: bases (1+i) G laid down in HBM by the library itself; uniform canonical Montgomery scalars
+    g = np.array(G1_GEN_MONT, dtype=np.uint64)
+    p0 = g.copy()
+    bases = torch.empty((n_loc, 12), dtype=torch.int64, device="cuda")
+    if beg:
+        # P0 = (1 + beg) G through the reference-named flat entry point, whose result is Jacobian in
+        # Montgomery form with Z = R, i.e. (x, y) already is the Montgomery affine point
+        s1 = np.array([[beg + 1, 0, 0, 0]], dtype=np.uint64)
+        res = np.zeros(18, dtype=np.uint64)
+        L.check(lib.bls12_381_g1_msm_cuda(L.ptr(s1), L.ptr(g), 1, C.byref(lib.b381_default_msm_config()), L.ptr(res)), "seed point")
+        p0 = res[:12].copy()
+    L.check(lib.b381_g1_point_series(L.ptr(p0), L.ptr(g), C.c_uint64(n_loc), L.ptr(bases), None), "point_series")
+    gen = torch.Generator(device="cuda").manual_seed(0xB12381 + rank)
+    sc = torch.randint(0, 1 << 62, (n_loc, 4), dtype=torch.int64, device="cuda", generator=gen) * 4 + \
+        torch.randint(0, 4, (n_loc, 4), dtype=torch.int64, device="cuda", generator=gen)
+    sc[:, 3] = torch.randint(0, R_TOP_LIMB, (n_loc,), dtype=torch.int64, device="cuda", generator=gen)
+    sc_host = torch.empty((n_loc, 4), dtype=torch.int64).pin_memory()
+    sc_host.copy_(sc)
+    torch.cuda.synchronize()
+
+    msm = D.ShardedMsm("g1")
+    result = {}
+
+    def step_resident():
+        part = msm.partial(sc, bases, n_loc, scalars_mont=True)
+        parts = D.gather_partials(part)
+        if rank == 0:
+            result["r"] = msm.combine(parts)
+
+    stage = torch.empty_like(sc)
+
+    def step_e2e():
+        stage.copy_(sc_host, non_blocking=True)          # H2D from pinned memory, inside the timed region
+        part = msm.partial(stage, bases, n_loc, scalars_mont=True)
+        parts = D.gather_partials(part)
+        if rank == 0:
+            result["e2e"] = msm.combine(parts)           # D2H of the 144-byte result
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k, phase_sink=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        for _ in range(k):
+            fn()
+            if phase_sink is not None:
+                buf = (C.c_float * 8)()
+                cnt = lib.b381_msm_last_timings(buf, 8)
+                phase_sink.append([buf[i] for i in range(cnt)])
+        e1.record()
+        barrier()
+        t1 = time.perf_counter()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), t0, t1
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    for _ in range(args.warmup):
+        step_resident()
+    phases = []
+    ms_total, t0, t1 = timed(step_resident, args.steps, phases)
+    clocks = sampler.window(t0, t1) if sampler else None
+    for _ in range(min(args.warmup, 2)):
+        step_e2e()
+    ms_e2e, _, _ = timed(step_e2e, args.steps)
+
+    # ---- NTT 2^24: every rank transforms its own resident vector (replicas; four-step is exercised by tests/dist)
+    ntt_ctx = M.GpuNttContext(args.log_n)
+    vec = sc.clone()                                   # canonical Montgomery words
+    vec_host = sc_host
+    ntt_out_host = torch.empty_like(sc_host).pin_memory() if n_loc == n else None
+
+    def ntt_step():
+        ntt_ctx.ntt_on_device(vec.data_ptr(), 0, size=n_loc if n_loc & (n_loc - 1) == 0 else n)
+
+    ntt_ok = n_loc & (n_loc - 1) == 0
+    ntt = None
+    if ntt_ok:
+        for _ in range(args.warmup):
+            ntt_step()
+        ntt_ms, _, _ = timed(ntt_step, args.steps)
+        ntt_ms /= args.steps
+        ntt_e2e = None
+        if ntt_out_host is not None:
+            def ntt_e2e_step():
+                vec.copy_(vec_host, non_blocking=True)
+                ntt_step()
+                ntt_out_host.copy_(vec, non_blocking=True)
+            ntt_e2e_step()
+            ms, _, _ = timed(ntt_e2e_step, max(1, args.steps // 2))
+            ntt_e2e = ms / max(1, args.steps // 2)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        passes = 1 if args.log_n <= 11 else (2 if args.log_n <= 20 else 3)
+        alg_bytes = 128.0 * n_loc          # 2^13..2^24 -> 128 B/element (two ideal passes)
+        ntt = {"metric": f"fr_ntt_2^{n_loc.bit_length() - 1}_elements_per_s", "value": n_loc * world / (ntt_ms * 1e-3),
+               "unit": "elements/s", "ms_per_step": ntt_ms, "scaling": "weak (one resident transform per GPU)" if world > 1 else "single",
+               "e2e": None if ntt_e2e is None else {"value": n_loc / (ntt_e2e * 1e-3), "unit": "elements/s",
+                                                     "h2d_bytes_per_step": n_loc * 32, "d2h_bytes_per_step": n_loc * 32},
+               "roofline": {"bound": "hbm", "achieved": alg_bytes / (ntt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                            "frac": alg_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                            "kernel": f"k_ntt_pass x{passes}", "note": "compute (IMAD) bound: see imad_frac"},
+               "gpu_launches": passes}
+
+    # ---- roofline denominators measured on this box, now (rank 0)
+    out = None
+    if rank == 0:
+        v, ms = C.c_double(), C.c_float()
+        L.check(lib.b381_bench_imad_peak(4000, C.byref(v), C.byref(ms)), "imad probe")
+        imad_peak = v.value
+        L.check(lib.b381_bench_field_mul(0, 1000, C.byref(v), C.byref(ms)), "fq probe")
+        fq_rate = v.value
+        L.check(lib.b381_bench_field_mul(1, 1000, C.byref(v), C.byref(ms)), "fr probe")
+        fr_rate = v.value
+        ms_step = ms_total / args.steps
+        ph = [statistics.mean(c) for c in zip(*phases)] if phases else []
+        names = ["digits", "sort", "offsets+tasks", "accumulate", "finalize", "bucket_reduce", "combine"]
+        acc_ms = ph[3] if len(ph) > 3 else None
+        # algorithmic work of the dominant kernel: one XYZZ mixed addition per (point, window) = 10 Fq
+        # multiplications x 300 32x32->64 multiply-adds; W = ceil(256/c), c = 16 at this size
+        W = 16 if args.log_n >= 21 else None
+        roof = None
+        if acc_ms and W:
+            mads = float(n_loc) * W * 10 * 300
+            ach = mads / (acc_ms * 1e-3)
+            roof = {"bound": "imad (integer pipe; neither HBM nor tensor)", "kernel": "k_msm_accumulate<fq_t>",
+                    "achieved": ach / 1e9, "peak": imad_peak / 1e9, "unit": "GMAD/s", "frac": ach / imad_peak,
+                    "traffic": None, "peak_source": "b381_bench_imad_peak, this run", "kernel_ms": acc_ms,
+                    "share_of_step": acc_ms / ms_step}
+        if ntt:
+            # n/2 * log2(n) butterflies, one Fr Montgomery product (2*8^2+8 = 136 multiply-adds) each
+            ln = n_loc.bit_length() - 1
+            ntt["roofline"]["imad_frac"] = (0.5 * n_loc * ln * 136) / (ntt["ms_per_step"] * 1e-3) / imad_peak
+        # one-off correctness check outside the timed region (oracle as checker): sum s_i (beg+1+i) G
+        check = "skipped"
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                from oracle import cref as O
+                from oracle import pyref as Pr
+                s_np = sc_host.numpy().view(np.uint64)
+                kk = np.zeros((n, 4), dtype=np.uint64)
+                kk[:, 0] = np.arange(1, n + 1, dtype=np.uint64)
+                dl = Pr.from_limbs(O.fr_dot(s_np, kk, s_mont=True))
+                exp = Pr.g1_result_std_bytes(Pr.g1_mul(dl, Pr.G1_GEN))
+                check = "ok" if result["r"].tobytes() == exp and result["e2e"].tobytes() == exp else "MISMATCH"
+            except Exception as e:  # noqa: BLE001
+                check = f"error: {e}"
+        cpu = None
+        if not args.no_cpu_baseline and world == 1:
+            cl = args.cpu_log_n or 18
+            r = cpu_leg(cl, 2, 0)
+            cpu = {"value": r["msm_pts_per_s"], "unit": "points/s", "cores": r["cores"], "kind": "port",
+                   "sample": f"G1 MSM 2^{cl} of the 2^{args.log_n} workload x2 (oracle/oracle.c, OpenMP); NTT 2^{r['ntt_log_n']}: "
+                             f"{r['ntt_elems_per_s']:.3e} elements/s"}
+        out = {
+            "metric": f"g1_msm_2^{args.log_n}_points_per_s", "value": n / (ms_step * 1e-3), "unit": "points/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64 (6x64 Fq / 4x64 Fr Montgomery, 32-bit IMAD limbs)",
+            "data": "synthetic",
+            "config": {"workload": f"G1 MSM n=2^{args.log_n}, bases (1+i)G resident in HBM, uniform Montgomery scalars; "
+                                   f"window c=16 signed digits; + Fr NTT 2^{args.log_n} (kNN, in place)",
+                       "sharding": f"{world} contiguous point ranges, one XYZZ partial per GPU, NCCL all_gather" if world > 1 else "single GPU",
+                       "l2": "inputs (0.5 GiB scalars + 1.5 GiB bases) exceed the 126 MB L2; no flush needed"},
+            "e2e": {"value": n / (ms_e2e / args.steps * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n_loc * 32,
+                    "d2h_bytes_per_step": 144, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": (11 + 10) * args.steps,
+            "gpu_launches_note": "own kernels per MSM step: digits, offsets, task_count, build_tasks, accumulate, finalize, "
+                                 "segment, 10x tree, combine, encode (CUB radix sort / scan kernels not counted)",
+            "phases_ms": dict(zip(names, [round(x, 4) for x in ph])),
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "ntt": ntt,
+            "probes": {"imad_wide_mad_per_s": imad_peak, "fq_mul_per_s": fq_rate, "fr_mul_per_s": fr_rate},
+            "result_check": check,
+        }
+    if sampler:
+        sampler.stop()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+
+
+if __name__ == "__main__":
+    main()

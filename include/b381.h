@@ -201,11 +201,27 @@ int b381_g1_msm_partial(const b381_fr* scalars, const b381_g1_affine* bases, int
                         const b381_msm_config* config, void* partial_xyzz_device);
 int b381_g2_msm_partial(const b381_fr* scalars, const b381_g2_affine* bases, int msm_size,
                         const b381_msm_config* config, void* partial_xyzz_device);
+/* Distributed four-step NTT, step 1 (north_star: "large NTTs use the four-step decomposition with an
+ * NCCL all-to-all").  A 2^log_n transform is spread over 2^log_gpus GPUs by COLUMN BLOCKS: with
+ * lo = log_n - upper_stages, GPU `rank` holds x[(i_hi << lo) | l] for every i_hi and l in
+ * [rank*L, (rank+1)*L), L = 2^lo / #GPUs, stored locally as [i_hi][l - rank*L].  This call runs the
+ * top `upper_stages` DIF stages in place (twiddles follow the global index).  The caller then
+ * exchanges row blocks (all-to-all) and finishes with b381_ntt(batch = 2^upper_stages / #GPUs,
+ * size = 2^lo, ordering kNR) -- see midnight_bls12_381_cuda_b200/dist.py. */
+int b381_ntt_dist_columns(b381_fr* data_device, int log_n, int log_gpus, int rank, int upper_stages, int dir, void* stream);
 /* Adds `count` XYZZ partials (device) and writes ONE ICICLE standard-form projective result. */
 int b381_g1_msm_combine(const void* partials_xyzz_device, int count, void* stream, bool result_on_device,
                         b381_g1_projective* result);
 int b381_g2_msm_combine(const void* partials_xyzz_device, int count, void* stream, bool result_on_device,
                         b381_g2_projective* result);
+
+/* ======================= base-set generation ======================= */
+/* out_device[i] = P0 + i*D as Montgomery affine points (P0, D: HOST pointers to one point each; out:
+ * DEVICE).  Lays down large distinct base sets with known discrete logs; conversion to affine is
+ * batched (one inversion per 16 points).  Reference counterpart: the per-point conversions of
+ * bls12-381/src/curve/point_ops.cu:61-101. */
+int b381_g1_point_series(const b381_g1_affine* p0, const b381_g1_affine* d, uint64_t n, b381_g1_affine* out_device, void* stream);
+int b381_g2_point_series(const b381_g2_affine* p0, const b381_g2_affine* d, uint64_t n, b381_g2_affine* out_device, void* stream);
 
 /* ======================= measurement helpers (bench.py / profiles) ======================= */
 /* Dependent-free IMAD.WIDE.U32 issue-rate probe: returns MAD/s through *mads_per_s. */

@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-I", CSRC, "-I", os.path.join(ROOT, "include"),
 ]
 
-CORE_SRCS = ["msm.cu", "ntt.cu", "vecops.cu", "devapi.cu", "probes.cu"]
+CORE_SRCS = ["msm.cu", "ntt.cu", "vecops.cu", "devapi.cu", "probes.cu", "pointgen.cu"]
 ICICLE_FIELD_SRCS = ["icicle/field_api.cu"]
 ICICLE_CURVE_SRCS = ["icicle/curve_api.cu", "icicle/g2_registry.cu"]
 ICICLE_DEVICE_SRCS = ["icicle/device_api.cu"]

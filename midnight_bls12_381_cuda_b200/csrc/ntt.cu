@@ -263,10 +263,54 @@ static int ntt_run(const fr_t* input, int size, int dir, const b381_ntt_config* 
   return B381_SUCCESS;
 }
 
+// Step 1 of the distributed (four-step) NTT: the top `a` stages of a 2^log_n transform on this
+// GPU's column block (see ntt_pass_params::dist_*), in place, device memory.
+static int ntt_dist_columns(fr_t* data, uint32_t log_n, uint32_t log_gpus, uint32_t rank, uint32_t a, int dir,
+                            cudaStream_t st) {
+  if (!data) return B381_INVALID_POINTER;
+  if (log_gpus == 0 || a == 0 || a + log_gpus > log_n || rank >= (1u << log_gpus)) return B381_INVALID_ARGUMENT;
+  const uint32_t lo = log_n - a;            // global bit where the column index ends
+  if (lo < log_gpus + 2) return B381_INVALID_ARGUMENT;   // keep >= 4 adjacent elements per tile row
+  const uint32_t logL = lo - log_gpus;
+  const uint32_t n_loc = log_n - log_gpus;
+  std::unique_lock<std::mutex> lk(g_dom_mu);
+  if (!g_dom.ready || log_n > g_dom.K) return B381_INVALID_ARGUMENT;
+  const fr_t* tw = g_dom.table;
+  // split the `a` upper stages into passes of <= 9 stages with g = min(tile - S, logL) adjacent columns
+  uint32_t rest = a, np = (a + 8) / 9, hi = n_loc;
+  for (uint32_t i = 0; i < np; i++) {
+    uint32_t S = (rest + (np - i) - 1) / (np - i);
+    ntt_pass_params p;
+    memset(&p, 0, sizeof(p));
+    p.n = n_loc; p.lo = hi - S; p.S = S;
+    p.g = kNttTileLog - S;
+    if (p.g > logL) p.g = logL;
+    if (p.g > p.lo) p.g = p.lo;
+    p.total = 1ull << n_loc;
+    p.estride = 1; p.bstride = 1ull << n_loc;
+    p.inverse = dir == B381_NTT_INVERSE;
+    p.twiddles = tw;
+    p.dist_shift = log_gpus; p.dist_logL = logL; p.dist_lo = lo; p.dist_lbase = rank << logL;
+    const uint32_t tile_log = p.S + p.g;
+    const uint64_t tiles = p.total >> tile_log;
+    cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(uint4) * kTile);
+    k_ntt_pass<<<(unsigned)tiles, kNttThreads, (size_t)2 * sizeof(uint4) << tile_log, st>>>(p, data, data);
+    hi -= S;
+    rest -= S;
+  }
+  lk.unlock();
+  return map_cuda_error(cudaGetLastError());
+}
+
 }  // namespace b381
 using namespace b381;
 
 extern "C" {
+int b381_ntt_dist_columns(b381_fr* data_device, int log_n, int log_gpus, int rank, int upper_stages, int dir, void* stream) {
+  if (log_n < 0 || log_gpus < 0 || rank < 0 || upper_stages < 0) return B381_INVALID_ARGUMENT;
+  return ntt_dist_columns((fr_t*)data_device, (uint32_t)log_n, (uint32_t)log_gpus, (uint32_t)rank, (uint32_t)upper_stages, dir,
+                          (cudaStream_t)stream);
+}
 int b381_ntt_init_domain(const b381_fr* root, const b381_ntt_init_domain_config* cfg) {
   if (!root) return B381_INVALID_POINTER;
   cudaStream_t st = cfg ? (cudaStream_t)cfg->stream : 0;

@@ -40,7 +40,21 @@ struct ntt_pass_params {
   const fr_t* post_scale; // optional: multiply logical output k by post_scale[k] on store (coset, inverse)
   fr_t post_const;        // used when has_post_const: multiply every output (1/N)
   uint32_t has_post_const;
+  // Distributed (multi-GPU, four-step) use: this GPU holds the column block l in [l_base, l_base+2^logL)
+  // of a 2^n_glob transform as a local array J = i_hi * 2^logL + (l - l_base); the pass runs on the
+  // local index space (n = n_glob - log2(#GPUs)) but twiddles follow the GLOBAL index.
+  uint32_t dist_shift;    // log2(#GPUs); 0 = single-GPU transform
+  uint32_t dist_logL;     // log2 of local columns
+  uint32_t dist_lo;       // global bit position where the column index ends (= dist_logL + dist_shift)
+  uint32_t dist_lbase;    // first global column owned by this GPU
 };
+
+// local flat index -> global flat index (identity when not distributed)
+B381_DI uint64_t ntt_global_index(const ntt_pass_params& p, uint64_t J) {
+  if (p.dist_shift == 0) return J;
+  uint64_t hi = J >> p.dist_logL, l = J & ((1ull << p.dist_logL) - 1);
+  return (hi << p.dist_lo) | (p.dist_lbase + l);
+}
 
 B381_HD uint32_t bitrev32(uint32_t v, uint32_t bits) {
 #if defined(__CUDA_ARCH__)
@@ -146,8 +160,8 @@ B381_DI void ntt_tile_stage(const ntt_pass_params& p, uint64_t tile_id, uint32_t
   uint32_t pos1 = pos0 | (1u << bit);
   uint64_t I0 = ntt_tile_index(p, tile_id, pos0);
   if (I0 >= p.total) return;
-  const uint32_t k = p.lo + s;
-  uint32_t j = (uint32_t)(I0 & ((1ull << k) - 1));    // i mod 2^k
+  const uint32_t k = p.lo + s + p.dist_shift;         // global stage
+  uint32_t j = (uint32_t)(ntt_global_index(p, I0) & ((1ull << k) - 1));    // i mod 2^k
   fr_t a = tile_get(t, pos0), b = tile_get(t, pos1);
   fr_t sum = add(a, b);
   fr_t d, w;
