@@ -145,17 +145,20 @@ static uint32_t ceil_log2_u64(uint64_t v) {
   return b;
 }
 
-// Window size: minimise  W * (10 n + 36 * 2^(c-1))  Fq-mul equivalents (bucket insertions +
-// bucket reduction), W = ceil((bits+1)/c).  Replaces get_optimal_c (include/msm.cuh:115-140).
+// Window size (replaces get_optimal_c, include/msm.cuh:115-140): minimise
+//   W * 10 n  +  Wf * 72 * 2^(c-1)      [Fq-mul equivalents: bucket insertions + bucket reduction]
+// with W = ceil((bits+1)/c), capped at c = 16: beyond that the per-bucket load (n / 2^(c-1)) gets so
+// small that warp divergence in the accumulate kernel eats the saving (measured on B200: 2^24 points,
+// c = 16 -> 130 ms, c = 20 -> 191 ms; profiles/r01_msm_window_sweep.txt).
 static uint32_t pick_window(uint32_t n, uint32_t bits, uint32_t factor) {
   const char* e = getenv("B381_MSM_C");
   if (e && atoi(e) > 0) return (uint32_t)atoi(e);
   double best = 1e300;
   uint32_t bc = 4;
-  for (uint32_t c = 4; c <= 22; c++) {
+  for (uint32_t c = 4; c <= 16; c++) {
     uint32_t W = (bits + 1 + c - 1) / c;
     uint32_t Wf = (W + factor - 1) / factor;
-    double cost = (double)W * 10.0 * n + (double)Wf * 36.0 * (double)(1u << (c - 1));
+    double cost = (double)W * 10.0 * n + (double)Wf * 72.0 * (double)(1u << (c - 1));
     if (cost < best) { best = cost; bc = c; }
   }
   return bc;
