@@ -31,6 +31,10 @@ class Block:
         self.nreg += 1
         return Reg(f"t{self.nreg - 1}")
 
+    def reg64(self) -> Reg:
+        self.nreg64 = getattr(self, "nreg64", 0) + 1
+        return Reg(f"d{self.nreg64 - 1}")
+
     def pred(self) -> Reg:
         self.npred += 1
         return Reg(f"p{self.npred - 1}")
@@ -49,6 +53,19 @@ class Block:
 
     def op4(self, op, a, b, c, dst=None):
         return self._e(op, dst or self.reg(), a, b, c)
+
+    def op2(self, op, a, dst=None):
+        return self._e(op, dst or self.reg(), a)
+
+    # 64-bit destinations
+    def w3(self, op, a, b):
+        return self._e(op, self.reg64(), a, b)
+
+    def w4(self, op, a, b, c):
+        return self._e(op, self.reg64(), a, b, c)
+
+    def w2(self, op, a):
+        return self._e(op, self.reg64(), a)
 
     def mov(self, a, dst=None):
         return self._e("mov.u32", dst or self.reg(), a)
@@ -81,15 +98,23 @@ class Block:
         return out
 
     # ---- interpreter ----
-    def run(self, env: dict[str, int]) -> dict[str, int]:
+    def run(self, env: dict[str, int], strict64: bool = False) -> dict[str, int]:
+        """strict64: raise if a 64-bit accumulate wraps (used to prove the no-overflow bounds)."""
         r = dict(env)
         cf = 0
+        M64 = (1 << 64) - 1
 
         def v(x):
             return (x & M32) if isinstance(x, int) else r[x]
 
         for op, dst, src in self.ins:
-            s = [v(x) for x in src] if op != "selm" else None
+            wide_src = op in ("add.u64", "shr.u64", "cvt.u32.u64")
+            if op == "selm" or wide_src:
+                s = None
+            elif op == "mad.wide.u32":
+                s = [v(src[0]), v(src[1])]
+            else:
+                s = [v(x) for x in src]
             if op == "mov.u32":
                 r[dst] = s[0]
             elif op == "mul.lo.u32":
@@ -135,6 +160,29 @@ class Block:
             elif op == "selm":
                 mask, a, b = src
                 r[dst] = v(a) if v(mask) != 0 else v(b)
+            elif op == "mul.wide.u32":
+                r[dst] = s[0] * s[1]
+            elif op == "mad.wide.u32":
+                t = s[0] * s[1] + r[src[2]]
+                if strict64 and t > M64:
+                    raise OverflowError(f"mad.wide wrapped: {dst}")
+                r[dst] = t & M64
+            elif op == "add.u64":
+                a64 = r[src[0]] if not isinstance(src[0], int) else src[0]
+                b64 = r[src[1]] if not isinstance(src[1], int) else src[1]
+                t = a64 + b64
+                if strict64 and t > M64:
+                    raise OverflowError(f"add.u64 wrapped: {dst}")
+                r[dst] = t & M64
+            elif op == "shr.u64":
+                r[dst] = r[src[0]] >> (src[1] if isinstance(src[1], int) else r[src[1]])
+            elif op == "cvt.u32.u64":
+                r[dst] = r[src[0]] & M32
+            elif op == "cvt.u64.u32":
+                r[dst] = s[0]
+            elif op == "shr.s32":
+                x = s[0] - (1 << 32) if s[0] >> 31 else s[0]
+                r[dst] = (x >> s[1]) & M32
             else:
                 raise NotImplementedError(op)
         return r

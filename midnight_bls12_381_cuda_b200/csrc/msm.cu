@@ -38,12 +38,27 @@ __global__ void k_msm_build_tasks(const uint32_t* offsets, const uint32_t* task_
   msm_build_tasks_body(b, offsets, task_start, nbuckets, K, tasks);
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_accumulate(const uint32_t* ntasks_dev, const uint2* tasks,
-                                                        const uint32_t* sorted_vals, const affine_t<F>* bases,
-                                                        xyzz_t<F>* partial) {
+template <class F, int MINB = 1>
+__global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* ntasks_dev, const uint2* tasks,
+                                                              const uint32_t* sorted_vals, const affine_t<F>* bases,
+                                                              xyzz_t<F>* partial) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   msm_accumulate_body<F>(t, *ntasks_dev, tasks, sorted_vals, bases, partial);
+}
+
+__global__ void __launch_bounds__(128, 3) k_msm_accumulate_lazy(const uint32_t* ntasks_dev, const uint2* tasks,
+                                                               const uint32_t* sorted_vals, const g1_affine* bases,
+                                                               g1_xyzz* partial) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_accumulate_lazy_body(t, *ntasks_dev, tasks, sorted_vals, bases, partial);
+}
+template <class F> static bool launch_lazy(unsigned, cudaStream_t, const uint32_t*, const uint2*, const uint32_t*, const affine_t<F>*, xyzz_t<F>*) { return false; }
+template <> bool launch_lazy<fq_t>(unsigned g, cudaStream_t st, const uint32_t* nt, const uint2* tasks, const uint32_t* sv,
+                                   const g1_affine* bases, g1_xyzz* partial) {
+  const char* e = getenv("B381_ACC_LAZY");
+  if (!e || e[0] != '1') return false;
+  k_msm_accumulate_lazy<<<g, 128, 0, st>>>(nt, tasks, sv, bases, partial);
+  return true;
 }
 
 template <class F>
@@ -232,7 +247,16 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   xyzz_t<F>*partial, *buckets;
   B381_CUDA_TRY(sc.alloc(&partial, max_tasks));
   B381_CUDA_TRY(sc.alloc(&buckets, (size_t)sh.nbuckets));
-  k_msm_accumulate<F><<<grid_for(max_tasks, 128), 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial);
+  {
+    int variant = 3;   // 166 registers -> 3 CTAs (12 warps) per SM: best of {1,3,4} on B200 (119.4 / 116.0 / 121.8 ms at 2^24)
+    const char* e = getenv("B381_ACC_MINB");
+    if (e) variant = atoi(e);
+    const unsigned g = grid_for(max_tasks, 128);
+    if (launch_lazy<F>(g, st, task_start + sh.nbuckets, tasks, svals, d_bases, partial)) {
+    } else if (variant == 3) k_msm_accumulate<F, 3><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial);
+    else if (variant == 4) k_msm_accumulate<F, 4><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial);
+    else k_msm_accumulate<F, 1><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial);
+  }
   tm.mark();
   // -- 6 finalize
   k_msm_finalize<F><<<grid_for(sh.nbuckets, 128), 128, 0, st>>>(sh.nbuckets, task_start, counts, partial, buckets);

@@ -22,6 +22,7 @@
 //                                                           [ref: :529-596 + icicle_curve_api.cu:134-229]
 #pragma once
 #include "curve.cuh"
+#include "fq_lazy.cuh"
 
 namespace b381 {
 
@@ -141,6 +142,27 @@ B381_DI void msm_accumulate_body(uint32_t t, uint32_t ntasks, const uint2* tasks
     xyzz_madd(acc, p);
   }
   partial[t] = acc;
+}
+
+// Experimental G1 variant (B381_ACC_LAZY=1): the same loop on carry-free lazy-reduced limbs
+// (fq_lazy.cuh).  Bit-exact, but on B200 it measured SLOWER than the saturated loop above (167 ms vs
+// 116 ms at 2^24): ptxas turns the mad.wide chains into products + 3-input adds (2.2x the instructions)
+// and the 64-bit-accumulate IMAD.WIDE issues at ~3.1 cycles here, so the heavy pipe saves nothing.
+// Kept selectable as evidence and as the starting point for a SASS-level version; see DESIGN.md.
+B381_DI void msm_accumulate_lazy_body(uint32_t t, uint32_t ntasks, const uint2* tasks, const uint32_t* sorted_vals,
+                                      const affine_t<fq_t>* bases, xyzz_t<fq_t>* partial) {
+  if (t >= ntasks) return;
+  uint2 tk = tasks[t];
+  g1_lazy_acc acc;
+  acc.inf = true;
+  for (uint32_t j = tk.x; j < tk.y; j++) {
+    uint32_t v = sorted_vals[j];
+    affine_t<fq_t> p = bases[v >> 1];
+    if (is_inf(p)) continue;
+    if (v & 1) p.y = neg(p.y);
+    lazy_madd(acc, p.x, p.y);
+  }
+  partial[t] = lazy_to_xyzz(acc);
 }
 
 // ---------------------------------------------------------------- 6 finalize
