@@ -38,26 +38,32 @@ __global__ void k_msm_build_tasks(const uint32_t* offsets, const uint32_t* task_
   msm_build_tasks_body(b, offsets, task_start, nbuckets, K, tasks);
 }
 
+__global__ void k_msm_task_keys(uint32_t max_tasks, const uint32_t* ntasks_dev, const uint2* tasks, uint32_t K,
+                                uint32_t* keys, uint32_t* ids) {
+  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  msm_task_key_body(t, max_tasks, *ntasks_dev, tasks, K, keys, ids);
+}
+
 template <class F, int MINB = 1>
 __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* ntasks_dev, const uint2* tasks,
                                                               const uint32_t* sorted_vals, const affine_t<F>* bases,
-                                                              xyzz_t<F>* partial) {
+                                                              xyzz_t<F>* partial, const uint32_t* order) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_accumulate_body<F>(t, *ntasks_dev, tasks, sorted_vals, bases, partial);
+  msm_accumulate_body<F>(t, *ntasks_dev, tasks, sorted_vals, bases, partial, order);
 }
 
 __global__ void __launch_bounds__(128, 3) k_msm_accumulate_lazy(const uint32_t* ntasks_dev, const uint2* tasks,
                                                                const uint32_t* sorted_vals, const g1_affine* bases,
-                                                               g1_xyzz* partial) {
+                                                               g1_xyzz* partial, const uint32_t* order) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_accumulate_lazy_body(t, *ntasks_dev, tasks, sorted_vals, bases, partial);
+  msm_accumulate_lazy_body(t, *ntasks_dev, tasks, sorted_vals, bases, partial, order);
 }
-template <class F> static bool launch_lazy(unsigned, cudaStream_t, const uint32_t*, const uint2*, const uint32_t*, const affine_t<F>*, xyzz_t<F>*) { return false; }
+template <class F> static bool launch_lazy(unsigned, cudaStream_t, const uint32_t*, const uint2*, const uint32_t*, const affine_t<F>*, xyzz_t<F>*, const uint32_t*) { return false; }
 template <> bool launch_lazy<fq_t>(unsigned g, cudaStream_t st, const uint32_t* nt, const uint2* tasks, const uint32_t* sv,
-                                   const g1_affine* bases, g1_xyzz* partial) {
+                                   const g1_affine* bases, g1_xyzz* partial, const uint32_t* order) {
   const char* e = getenv("B381_ACC_LAZY");
   if (!e || e[0] != '1') return false;
-  k_msm_accumulate_lazy<<<g, 128, 0, st>>>(nt, tasks, sv, bases, partial);
+  k_msm_accumulate_lazy<<<g, 128, 0, st>>>(nt, tasks, sv, bases, partial, order);
   return true;
 }
 
@@ -241,6 +247,28 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   uint2* tasks;
   B381_CUDA_TRY(sc.alloc(&tasks, max_tasks));
   k_msm_build_tasks<<<grid_for(sh.nbuckets, 256), 256, 0, st>>>(offsets, task_start, sh.nbuckets, K, tasks);
+  // visiting order: longest task first (radix sort of K - len over just enough bits), so the 32 tasks of a
+  // warp have near-equal lengths and the grid's tail is made of the shortest ones
+  const uint32_t* order = nullptr;
+  {
+    const char* e = getenv("B381_MSM_NO_TASK_SORT");
+    if (!(e && e[0] == '1')) {
+      uint32_t *tk[2], *ti[2];
+      for (int i = 0; i < 2; i++) {
+        B381_CUDA_TRY(sc.alloc(&tk[i], max_tasks));
+        B381_CUDA_TRY(sc.alloc(&ti[i], max_tasks));
+      }
+      k_msm_task_keys<<<grid_for(max_tasks, 256), 256, 0, st>>>((uint32_t)max_tasks, task_start + sh.nbuckets, tasks, K, tk[0], ti[0]);
+      cub::DoubleBuffer<uint32_t> bk(tk[0], tk[1]), bi(ti[0], ti[1]);
+      int bits = (int)ceil_log2_u64((uint64_t)K + 2);
+      size_t tb = 0;
+      B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, bk, bi, (int)max_tasks, 0, bits, st));
+      uint8_t* ttmp = nullptr;
+      B381_CUDA_TRY(sc.alloc(&ttmp, tb));
+      B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ttmp, tb, bk, bi, (int)max_tasks, 0, bits, st));
+      order = bi.Current();
+    }
+  }
   tm.mark();
 
   // -- 5 accumulate
@@ -252,10 +280,10 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
     const char* e = getenv("B381_ACC_MINB");
     if (e) variant = atoi(e);
     const unsigned g = grid_for(max_tasks, 128);
-    if (launch_lazy<F>(g, st, task_start + sh.nbuckets, tasks, svals, d_bases, partial)) {
-    } else if (variant == 3) k_msm_accumulate<F, 3><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial);
-    else if (variant == 4) k_msm_accumulate<F, 4><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial);
-    else k_msm_accumulate<F, 1><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial);
+    if (launch_lazy<F>(g, st, task_start + sh.nbuckets, tasks, svals, d_bases, partial, order)) {
+    } else if (variant == 3) k_msm_accumulate<F, 3><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial, order);
+    else if (variant == 4) k_msm_accumulate<F, 4><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial, order);
+    else k_msm_accumulate<F, 1><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial, order);
   }
   tm.mark();
   // -- 6 finalize

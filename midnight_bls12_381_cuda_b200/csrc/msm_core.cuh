@@ -127,10 +127,24 @@ B381_DI void msm_build_tasks_body(uint32_t b, const uint32_t* offsets, const uin
   }
 }
 
+// sort key of task t for the longest-first visiting order: K - len (valid), K + 1 (unused slot)
+B381_DI void msm_task_key_body(uint32_t t, uint32_t max_tasks, uint32_t ntasks, const uint2* tasks, uint32_t K,
+                               uint32_t* keys, uint32_t* ids) {
+  if (t >= max_tasks) return;
+  uint32_t key = K + 1;
+  if (t < ntasks) {
+    uint2 tk = tasks[t];
+    key = K - (tk.y - tk.x);
+  }
+  keys[t] = key;
+  ids[t] = t;
+}
+
 // ---------------------------------------------------------------- 5 accumulate (hot)
 template <class F>
 B381_DI void msm_accumulate_body(uint32_t t, uint32_t ntasks, const uint2* tasks, const uint32_t* sorted_vals,
-                                 const affine_t<F>* bases, xyzz_t<F>* partial) {
+                                 const affine_t<F>* bases, xyzz_t<F>* partial, const uint32_t* order = nullptr) {
+  if (order) t = order[t];              // tasks visited longest-first so a warp's 32 tasks have similar lengths
   if (t >= ntasks) return;
   uint2 tk = tasks[t];
   xyzz_t<F> acc = xyzz_identity<F>();
@@ -150,7 +164,8 @@ B381_DI void msm_accumulate_body(uint32_t t, uint32_t ntasks, const uint2* tasks
 // and the 64-bit-accumulate IMAD.WIDE issues at ~3.1 cycles here, so the heavy pipe saves nothing.
 // Kept selectable as evidence and as the starting point for a SASS-level version; see DESIGN.md.
 B381_DI void msm_accumulate_lazy_body(uint32_t t, uint32_t ntasks, const uint2* tasks, const uint32_t* sorted_vals,
-                                      const affine_t<fq_t>* bases, xyzz_t<fq_t>* partial) {
+                                      const affine_t<fq_t>* bases, xyzz_t<fq_t>* partial, const uint32_t* order = nullptr) {
+  if (order) t = order[t];
   if (t >= ntasks) return;
   uint2 tk = tasks[t];
   g1_lazy_acc acc;
