@@ -259,7 +259,7 @@ def main():
     ms_e2e, _, _ = timed(step_e2e, args.steps)
 
     # ---- NTT 2^24: every rank transforms its own resident vector (replicas; four-step is exercised by tests/dist)
-    ntt_ctx = M.GpuNttContext(args.log_n)
+    ntt_ctx = M.GpuNttContext(args.log_n, device_id=local_rank)
     vec = sc.clone()                                   # canonical Montgomery words
     vec_host = sc_host
     ntt_out_host = torch.empty_like(sc_host).pin_memory() if n_loc == n else None
