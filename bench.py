@@ -10,8 +10,9 @@ One JSON line on rank 0 (contract in the task statement / DESIGN.md "Measurement
                 all_gather, combine); the NTT 2^24 is timed right after it and reported under "ntt".
   * value     = points/s with scalars already in HBM;  e2e = same through the public API with HOST
                 (pinned) scalars, H2D inside the timed region, result read back to the host.
-  * roofline  = k_msm_accumulate against the IMAD.WIDE issue peak MEASURED in this run (the path is
-                integer-pipe bound, not HBM/tensor); "ntt.roofline" is the HBM view north_star asks for.
+  * roofline  = bucket accumulation (affine pre-reduction levels + k_msm_accumulate) against the IMAD.WIDE issue
+                peak MEASURED in this run (the path is integer-pipe bound, not HBM/tensor); "ntt.roofline" is the
+                HBM view north_star asks for.
   * cpu_baseline / --impl reference = the CPU port oracle/oracle.c (BLST / midnight-curves are not in
     this image: kind "port") on a bounded sample with every host core.
 The oracle is used here ONLY for that CPU leg and for a one-off result check outside the timed region.
@@ -36,6 +37,12 @@ G1_GEN_MONT = [0x5cb38790fd530c16, 0x7817fc679976fff5, 0x154f95c7143ba1c1, 0xf0a
                0x120177419e0bfb75, 0xbaac93d50ce72271, 0x8c22631a7918fd8e, 0xdd595f13570725ce, 0x51ac582950405194,
                0x0e1c8c3fad0059c0, 0x0bbc3efc5008a26a]
 R_TOP_LIMB = 0x73EDA753299D7D48
+# G2 generator, Montgomery affine (x.c0, x.c1, y.c0, y.c1), spec constant
+G2_GEN_MONT = [0xf5f28fa202940a10, 0xb3f5fb2687b4961a, 0xa1a893b53e2ae580, 0x9894999d1a3caee9, 0x6f67b7631863366b,
+               0x58191924350bcd7, 0xa5a9c0759e23f606, 0xaaa0c59dbccd60c3, 0x3bb17e18e2867806, 0x1b1ab6cc8541b367,
+               0xc2b6ed0ef2158547, 0x11922a097360edf3, 0x4c730af860494c4a, 0x597cfa1f5e369c5a, 0xe7e6856caa0a635a,
+               0xbbefb5e96e0d495f, 0x7d3a975f0ef25a2, 0x83fd8e7e80dae5, 0xadc0fc92df64b05d, 0x18aa270a2b1461dc,
+               0x86adac6a3be4eba0, 0x79495c4ec93da33a, 0xe7175850a43ccaed, 0xb2bc2a163de1bf2]
 
 
 def parse():
@@ -237,8 +244,8 @@ def main():
         for _ in range(k):
             fn()
             if phase_sink is not None:
-                buf = (C.c_float * 8)()
-                cnt = lib.b381_msm_last_timings(buf, 8)
+                buf = (C.c_float * 12)()
+                cnt = lib.b381_msm_last_timings(buf, 12)
                 phase_sink.append([buf[i] for i in range(cnt)])
         e1.record()
         barrier()
@@ -302,6 +309,29 @@ def main():
                "gpu_launches": passes}
 
     # ---- roofline denominators measured on this box, now (rank 0)
+    # ---- G2 MSM 2^20 (BASELINE.json config 4), single GPU only: bases (1+i) G2 resident, first 2^20 scalars
+    g2 = None
+    if world == 1 and args.log_n >= 20:
+        n2 = 1 << 20
+        g2g = np.array(G2_GEN_MONT, dtype=np.uint64)
+        bases2 = torch.empty((n2, 24), dtype=torch.int64, device="cuda")
+        L.check(lib.b381_g2_point_series(L.ptr(g2g), L.ptr(g2g), C.c_uint64(n2), L.ptr(bases2), None), "g2 point_series")
+        cfg2 = lib.b381_default_msm_config()
+        cfg2.are_scalars_on_device = cfg2.are_points_on_device = True
+        cfg2.are_scalars_montgomery_form = cfg2.are_points_montgomery_form = True
+        res2 = np.zeros(36, dtype=np.uint64)
+
+        def g2_step():
+            L.check(lib.b381_g2_msm(L.ptr(sc), L.ptr(bases2), n2, C.byref(cfg2), L.ptr(res2)), "g2 msm")
+        for _ in range(2):
+            g2_step()
+        g2_phases = []
+        g2_ms, _, _ = timed(g2_step, args.steps, g2_phases)
+        g2_ms /= args.steps
+        g2 = {"metric": "g2_msm_2^20_points_per_s", "value": n2 / (g2_ms * 1e-3), "unit": "points/s", "ms_per_step": g2_ms,
+              "phases_ms": [round(statistics.mean(c), 4) for c in zip(*g2_phases)], "result": res2}
+        del bases2
+
     out = None
     if rank == 0:
         v, ms = C.c_double(), C.c_float()
@@ -313,19 +343,28 @@ def main():
         fr_rate = v.value
         ms_step = ms_total / args.steps
         ph = [statistics.mean(c) for c in zip(*phases)] if phases else []
-        names = ["digits", "sort", "offsets+tasks", "accumulate", "finalize", "bucket_reduce", "combine"]
-        acc_ms = ph[3] if len(ph) > 3 else None
-        # algorithmic work of the dominant kernel: one XYZZ mixed addition per (point, window) = 10 Fq
-        # multiplications x 300 32x32->64 multiply-adds; W = ceil(256/c), c = 16 at this size
-        W = 16 if args.log_n >= 21 else None
+        names = ["digits", "sort", "offsets", "prereduce", "tasks+accumulate", "finalize", "bucket_reduce", "combine"]
+        info = (C.c_int * 4)()
+        lib.b381_msm_last_info(info, 4)
+        c_win, W, levels, own_launches = info[0], info[1], info[2], info[3]
+        # Dominant stage = bucket accumulation: `levels` affine pre-reduction levels (k_msm_pair_fwd / k_msm_invert_totals /
+        # k_msm_pair_bwd, csrc/msm_batch.cuh) + k_msm_accumulate on what is left.  Algorithmic work per (point, window)
+        # insertion as SURVEY.md 8d defines it: one XYZZ mixed addition = 10 Fq products x 300 32x32->64 multiply-adds.
+        # The affine levels EXECUTE 6 products per insertion instead; "executed_frac" is the pipe-level figure.
+        acc_ms = (ph[3] + ph[4]) if len(ph) > 4 else None
         roof = None
         if acc_ms and W:
-            mads = float(n_loc) * W * 10 * 300
-            ach = mads / (acc_ms * 1e-3)
-            roof = {"bound": "imad (integer pipe; neither HBM nor tensor)", "kernel": "k_msm_accumulate<fq_t>",
+            ins = float(n_loc) * W
+            ach = ins * 3000.0 / (acc_ms * 1e-3)
+            frac_removed = 1.0 - 0.5 ** levels
+            executed = ins * (frac_removed * 6 + (1.0 - frac_removed) * 10) * 300.0 / (acc_ms * 1e-3)
+            roof = {"bound": "imad (integer pipe; neither HBM nor tensor)",
+                    "kernel": f"bucket accumulation: {levels} x (k_msm_pair_fwd, k_msm_invert_totals, k_msm_pair_bwd) + k_msm_accumulate<fq_t>",
                     "achieved": ach / 1e9, "peak": imad_peak / 1e9, "unit": "GMAD/s", "frac": ach / imad_peak,
+                    "executed_frac": executed / imad_peak,
+                    "algorithmic_unit": "3000 MAD per (point, window) insertion (SURVEY.md 8d); executed: 1800 in the affine levels",
                     "traffic": None, "peak_source": "b381_bench_imad_peak, this run", "kernel_ms": acc_ms,
-                    "share_of_step": acc_ms / ms_step}
+                    "share_of_step": acc_ms / ms_step, "window_c": c_win, "windows": W, "affine_levels": levels}
         if ntt:
             # n/2 * log2(n) butterflies, one Fr Montgomery product (2*8^2+8 = 136 multiply-adds) each
             ln = n_loc.bit_length() - 1
@@ -342,6 +381,12 @@ def main():
                 dl = Pr.from_limbs(O.fr_dot(s_np, kk, s_mont=True))
                 exp = Pr.g1_result_std_bytes(Pr.g1_mul(dl, Pr.G1_GEN))
                 check = "ok" if result["r"].tobytes() == exp and result["e2e"].tobytes() == exp else "MISMATCH"
+                if g2 is not None:
+                    kk2 = np.zeros((1 << 20, 4), dtype=np.uint64)
+                    kk2[:, 0] = np.arange(1, (1 << 20) + 1, dtype=np.uint64)
+                    dl2 = Pr.from_limbs(O.fr_dot(s_np[:1 << 20], kk2, s_mont=True))
+                    exp2 = Pr.g2_result_std_bytes(Pr.g2_mul(dl2, Pr.G2_GEN))
+                    g2["result_check"] = "ok" if g2["result"].tobytes() == exp2 else "MISMATCH"
             except Exception as e:  # noqa: BLE001
                 check = f"error: {e}"
         cpu = None
@@ -357,17 +402,19 @@ def main():
             "scaling": "strong", "vs_baseline": None, "dtype": "u64 (6x64 Fq / 4x64 Fr Montgomery, 32-bit IMAD limbs)",
             "data": "synthetic",
             "config": {"workload": f"G1 MSM n=2^{args.log_n}, bases (1+i)G resident in HBM, uniform Montgomery scalars; "
-                                   f"window c=16 signed digits; + Fr NTT 2^{args.log_n} (kNN, in place)",
+                                   f"window c={c_win} signed digits, {levels} affine pre-reduction levels; + Fr NTT 2^{args.log_n} (kNN, in place)",
                        "sharding": f"{world} contiguous point ranges, one XYZZ partial per GPU, NCCL all_gather" if world > 1 else "single GPU",
                        "l2": "inputs (0.5 GiB scalars + 1.5 GiB bases) exceed the 126 MB L2; no flush needed"},
             "e2e": {"value": n / (ms_e2e / args.steps * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n_loc * 32,
                     "d2h_bytes_per_step": 144, "ms_per_step": ms_e2e / args.steps,
                     "note": "pinned-host scalars; H2D of step i+1 overlaps compute of step i (copy stream, 2 staging buffers)"},
-            "gpu_launches": (11 + 10) * args.steps,
-            "gpu_launches_note": "own kernels per MSM step: digits, offsets, task_count, build_tasks, accumulate, finalize, "
-                                 "segment, 10x tree, combine, encode (CUB radix sort / scan kernels not counted)",
+            "gpu_launches": (own_launches + 1) * args.steps,
+            "gpu_launches_note": "own kernels per MSM step as counted by the library (b381_msm_last_info): digits, offsets, "
+                                 "4 per affine level, task_count/build_tasks/task_keys, accumulate, finalize, segment, tree levels, "
+                                 "combine, + encode (CUB radix sort / scan kernels not counted)",
             "phases_ms": dict(zip(names, [round(x, 4) for x in ph])),
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "ntt": ntt,
+            "g2": None if g2 is None else {k: v for k, v in g2.items() if k != "result"},
             "probes": {"imad_wide_mad_per_s": imad_peak, "fq_mul_per_s": fq_rate, "fr_mul_per_s": fr_rate},
             "result_check": check,
         }

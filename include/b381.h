@@ -228,9 +228,12 @@ int b381_g2_point_series(const b381_g2_affine* p0, const b381_g2_affine* d, uint
 int b381_bench_imad_peak(int iters, double* mads_per_s, float* ms);
 /* Back-to-back Montgomery multiplications per thread (throughput of fq/fr mul in isolation). */
 int b381_bench_field_mul(int field /*0=fq,1=fr*/, int iters, double* muls_per_s, float* ms);
-/* last kernel-level timing breakdown of the most recent MSM on this thread, ms per phase:
- * [digits, sort, offsets+tasks, accumulate, finalize, reduce, combine]; returns count written. */
+/* last kernel-level timing breakdown of the most recent MSM on this thread (B381_MSM_TIMING=1), ms per phase:
+ * [digits, sort, offsets, affine pre-reduction, tasks+accumulate, finalize, reduce, combine]; returns count written. */
 int b381_msm_last_timings(float* out, int cap);
+/* shape of the most recent MSM on this thread: [window bits c, windows W, affine pre-reduction levels,
+ * own kernel launches]; returns count written. */
+int b381_msm_last_info(int* out, int cap);
 const char* b381_version(void);
 
 #ifdef __cplusplus

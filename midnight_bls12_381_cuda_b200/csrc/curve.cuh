@@ -131,7 +131,7 @@ template <class F> B381_DI xyzz_t<F> xyzz_neg(const xyzz_t<F>& p) { return xyzz_
 //   derive 1/ZZ = (1/ZZZ)^2 * ZZ^2 ... (ZZ^2/ZZZ^2 = ZZ^2/ZZ^3 = 1/ZZ).
 template <class F> B381_DI affine_t<F> xyzz_to_affine(const xyzz_t<F>& p) {
   if (is_inf(p)) return affine_t<F>{zero<F>(), zero<F>()};
-  F iz3 = inv(p.zzz);
+  F iz3 = inv_vartime(p.zzz);   // public data; ~6x shorter than a^(p-2) on a lone thread
   F t = mul(iz3, p.zz);      // ZZ/ZZZ
   F iz2 = sqr(t);            // ZZ^2/ZZZ^2 = 1/ZZ
   return affine_t<F>{mul(p.x, iz2), mul(p.y, iz3)};

@@ -82,6 +82,97 @@ B381_DI F pow_m_minus_2(const F& a, const uint64_t (&m)[N64]) {
 B381_DI fq_t inv(const fq_t& a) { const uint64_t m[6] = FQ_MODULUS_INIT; return pow_m_minus_2<fq_t, 6>(a, m); }
 B381_DI fr_t inv(const fr_t& a) { const uint64_t m[4] = FR_MODULUS_INIT; return pow_m_minus_2<fr_t, 4>(a, m); }
 
+// ---- variable-time inversion (Kaliski almost-inverse + 3 Montgomery products) -------------------
+// Used by the batched inversions of the affine bucket pre-reduction (msm_batch.cuh): ~560 rounds of
+// 384-bit shift/subtract instead of the ~760 dependent Montgomery products of a^(m-2).  Public data
+// only (MSM bases).  Phase 1 leaves x = A^-1 * 2^k (mod p), 381 <= k <= 762, for the integer A = a*R
+// held in `a`; a^-1 * R = x * 2^(768-k), applied as mont(mont(mont(x, R^3), 2^e2), 2^e3), e2+e3 = 768-k.
+//
+// The round is written for SIMT: u stays odd, only v is halved, and the "v < u" case swaps the roles
+// of (u,r) and (v,s) with masks, so every lane of a warp runs the same instructions whatever its
+// value -- the textbook four-way branch made a warp of 32 different inversions execute all four arms
+// every round (ncu: 211 k instructions per warp-inversion).  Invariants, sigma = +-1 flipping on a swap:
+//   u*s + v*r = p,   a*r = -sigma*u*2^k,   a*s = sigma*v*2^k  (mod p).
+B381_HD uint64_t raw6_add(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  unsigned __int128 c = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) { c += (unsigned __int128)a[i] + b[i]; r[i] = (uint64_t)c; c >>= 64; }
+  return (uint64_t)c;
+}
+B381_HD uint64_t raw6_sub(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+  uint64_t br = 0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    unsigned __int128 d = (unsigned __int128)a[i] - b[i] - br;
+    r[i] = (uint64_t)d;
+    br = (uint64_t)(d >> 64) & 1;
+  }
+  return br;
+}
+B381_HD void raw6_shr1(uint64_t* a) {
+#pragma unroll
+  for (int i = 0; i < 5; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 63);
+  a[5] >>= 1;
+}
+B381_HD void raw6_shl1(uint64_t* a) {
+#pragma unroll
+  for (int i = 5; i > 0; i--) a[i] = (a[i] << 1) | (a[i - 1] >> 63);
+  a[0] <<= 1;
+}
+B381_DI fq_t inv_vartime(const fq_t& a) {
+  if (is_zero(a)) return a;
+  const uint64_t P[6] = FQ_MODULUS_INIT;
+  uint64_t u[6], v[6], r[6], s[6], t1[6], t2[6], ss[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) { u[i] = P[i]; v[i] = a.l[i]; r[i] = 0; s[i] = 0; }
+  s[0] = 1;
+  uint32_t k = 0;
+  uint64_t sigma_neg = 0;
+#pragma unroll 1
+  while ((v[0] | v[1] | v[2] | v[3] | v[4] | v[5]) != 0) {
+    const uint64_t odd = 0 - (v[0] & 1);
+    const uint64_t lt = raw6_sub(t1, v, u);      // t1 = v - u, borrow <=> v < u
+    raw6_sub(t2, u, v);                          // t2 = u - v
+    raw6_add(ss, r, s);
+    const uint64_t swp = odd & (0 - lt);
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+      uint64_t vn = (t1[i] & ~swp) | (t2[i] & swp);
+      uint64_t vi = (v[i] & ~odd) | (vn & odd);
+      u[i] = (u[i] & ~swp) | (v[i] & swp);
+      uint64_t rn = (r[i] & ~swp) | (s[i] & swp);
+      s[i] = (s[i] & ~odd) | (ss[i] & odd);
+      r[i] = rn;
+      v[i] = vi;
+    }
+    raw6_shr1(v);
+    raw6_shl1(r);
+    sigma_neg ^= swp & 1;
+    k++;
+  }
+  if (raw6_sub(t1, r, P) == 0) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) r[i] = t1[i];
+  }
+  fq_t x;
+  if (sigma_neg) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) x.l[i] = r[i];
+  } else {
+    raw6_sub(x.l, P, r);
+  }
+  uint32_t e = 768u - k, e2 = e > 380u ? 380u : e, e3 = e - e2;
+  fq_t c2 = zero<fq_t>(), c3 = zero<fq_t>();
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    if ((e2 >> 6) == (uint32_t)i) c2.l[i] = 1ull << (e2 & 63);
+    if ((e3 >> 6) == (uint32_t)i) c3.l[i] = 1ull << (e3 & 63);
+  }
+  x = mul(x, fq_t{FQ_R3_INIT});
+  x = mul(x, c2);
+  return mul(x, c3);
+}
+
 // r = a^e for a 64-bit exponent (twiddle / coset power setup)
 template <class F>
 B381_DI F pow_u64(const F& a, uint64_t e) {
@@ -122,6 +213,10 @@ B381_DI bool is_zero(const fq2_t& a) { return is_zero(a.c0) && is_zero(a.c1); }
 B381_DI bool eq(const fq2_t& a, const fq2_t& b) { return eq(a.c0, b.c0) && eq(a.c1, b.c1); }
 B381_DI fq2_t inv(const fq2_t& a) {
   fq_t n = inv(add(sqr(a.c0), sqr(a.c1)));
+  return fq2_t{mul(a.c0, n), neg(mul(a.c1, n))};
+}
+B381_DI fq2_t inv_vartime(const fq2_t& a) {
+  fq_t n = inv_vartime(add(sqr(a.c0), sqr(a.c1)));
   return fq2_t{mul(a.c0, n), neg(mul(a.c1, n))};
 }
 B381_DI fq2_t to_mont(const fq2_t& a) { return fq2_t{to_mont(a.c0), to_mont(a.c1)}; }

@@ -270,6 +270,7 @@ def constants() -> str:
         out.append(f"#define {N}_MODULUS_INIT {_c64(f.m, n64)}")
         out.append(f"#define {N}_ONE_INIT {_c64(f.R, n64)}        /* R mod m */")
         out.append(f"#define {N}_R2_INIT {_c64(f.R2, n64)}         /* R^2 mod m */")
+        out.append(f"#define {N}_R3_INIT {_c64(f.R2 * f.R % f.m, n64)}         /* R^3 mod m */")
         out.append(f"#define {N}_INV32 0x{f.m0:08x}u          /* -m^-1 mod 2^32 */")
     g1x = 0x17F1D3A73197D7942695638C4FA9AC0FC3688C4F9774B905A14E3A3F171BAC586C55E83FF97A1AEFFB3AF00ADB22C6BB
     g1y = 0x08B3F481E3AAA0F1A09E30ED741D8AE4FCF5E095D5D00AF600DB18CB2C04B3EDD03CC744A2888AE40CAA232946C5E7E1

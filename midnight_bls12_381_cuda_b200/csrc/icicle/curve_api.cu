@@ -1,6 +1,6 @@
 // ICICLE registration of the G1/G2 MSM for device type "CUDA".
 // Takes the place of bls12-381/src/backend/icicle_curve_api.cu:243-665: the callbacks forward to the
-// C ABI (b381_g1_msm & co. in msm.cu), which implements the config-flag semantics (host/device
+// C ABI (b381_g1_msm & co. in msm_impl.cuh), which implements the config-flag semantics (host/device
 // residency, Montgomery flags, batch, precompute_factor, async).
 #include "icicle_abi.h"
 

@@ -1,0 +1,204 @@
+// Affine bucket pre-reduction with batched inversion (G1 and G2) -- per-thread bodies.
+//
+// After the sort every bucket is a contiguous run of (point, sign) entries.  One LEVEL replaces
+// each bucket of s points by ceil(s/2) points: neighbours (2i, 2i+1) are added in AFFINE
+// coordinates, lambda = (y2-y1)/(x2-x1), the denominators inverted together with Montgomery's
+// trick: 3 products per pair for the shared inversion + 2M + 1S for the addition =
+// 6 Fq products per removed point, against 10 (8M+2S) for the XYZZ mixed addition the serial
+// accumulate kernel spends -- and the work is spread by OUTPUT SLOT, not by bucket, so it is
+// balanced whatever the scalar distribution.  After a few levels the buckets are short and the
+// existing task/accumulate/finalize path finishes them.
+//
+// The reference has no counterpart: it accumulates in Jacobian coordinates with an add that also
+// evaluates a doubling every time (bls12-381/src/curve/msm_kernels.cu:269-366,
+// include/point.cuh:803-912).  The affine result of the MSM is representation independent, so
+// bit-exactness against the oracle is unaffected.
+//
+// One thread owns B consecutive output slots.  Three kernels per level, no barrier anywhere:
+//   k_msm_pair_fwd     walk the slots (slot -> input pair), denominators, running product; the exclusive
+//                      prefixes and the thread's total go to global memory (slot-major, coalesced)
+//   k_msm_invert_totals  Montgomery's trick once more over M totals per thread + ONE variable-time
+//                      inversion per thread (field.cuh inv_vartime): ~3.4 products per total
+//   k_msm_pair_bwd     walk backward: 1/d_k = inv * prefix_k, inv *= d_k, finish the affine addition
+// (A first version inverted once per CTA behind __syncthreads; ncu showed the barrier as the top stall
+// and the IMAD pipe 50 % busy, so the inversion moved into its own kernel.)
+#pragma once
+#include "curve.cuh"
+
+namespace b381 {
+
+// launch shape of the per-level kernels (msm_pair.cu) and slots per thread / max totals per inversion
+constexpr int PR_TPB = 128;
+template <class F> struct pair_batch { static constexpr int B = 32, M = 64; };
+template <> struct pair_batch<fq2_t> { static constexpr int B = 16, M = 32; };
+
+enum : uint32_t { PAIR_NONE = 0xFFFFFFFFu, PAIR_SINGLE = 0x80000000u };
+enum : int { PK_COPY_P = 0, PK_COPY_Q = 1, PK_INF = 2, PK_ADD = 3, PK_DBL = 4 };
+
+// point at sorted position `pos` of the current level; level 0 gathers through the sorted
+// (index, sign) entries and applies the sign
+template <class F, bool L0>
+B381_DI affine_t<F> pair_load(uint32_t pos, const uint32_t* svals, const affine_t<F>* pts) {
+  if (L0) {
+    uint32_t v = svals[pos];
+    affine_t<F> p = pts[v >> 1];
+    if ((v & 1) && !is_inf(p)) p.y = neg(p.y);
+    return p;
+  }
+  return pts[pos];
+}
+
+// what P + Q needs, and the denominator that goes into the batched inversion
+template <class F>
+B381_DI int pair_classify(const affine_t<F>& p, const affine_t<F>& q, F& denom) {
+  denom = one<F>();
+  if (is_inf(q)) return PK_COPY_P;
+  if (is_inf(p)) return PK_COPY_Q;
+  F dx = sub(q.x, p.x);
+  if (is_zero(dx)) {
+    if (!eq(p.y, q.y)) return PK_INF;       // P + (-P)
+    denom = dbl(p.y);                        // y != 0 on a curve without 2-torsion
+    return PK_DBL;
+  }
+  denom = dx;
+  return PK_ADD;
+}
+
+template <class F>
+B381_DI affine_t<F> pair_finish(int kind, const affine_t<F>& p, const affine_t<F>& q, const F& dinv) {
+  if (kind == PK_COPY_P) return p;
+  if (kind == PK_COPY_Q) return q;
+  if (kind == PK_INF) return affine_t<F>{zero<F>(), zero<F>()};
+  F num;
+  if (kind == PK_ADD) num = sub(q.y, p.y);
+  else { F x2 = sqr(p.x); num = add(dbl(x2), x2); }
+  F lam = mul(num, dinv);
+  affine_t<F> r;
+  r.x = sub(sub(sqr(lam), p.x), q.x);
+  r.y = sub(mul(lam, sub(p.x, r.x)), p.y);
+  return r;
+}
+
+// ceil(size/2) per bucket; the exclusive scan of these is the next level's offsets
+B381_DI void msm_half_counts_body(uint32_t b, const uint32_t* offsets, uint32_t nbuckets, uint32_t* counts) {
+  if (b > nbuckets) return;
+  counts[b] = b < nbuckets ? (offsets[b + 1] - offsets[b] + 1) / 2 : 0u;
+}
+
+// slot -> input pair.  src[k*stride] = position of the pair's first point (| PAIR_SINGLE when the bucket's
+// odd last point is just carried over), PAIR_NONE past the end.
+template <int B>
+B381_DI void pair_walk(uint32_t slot0, uint32_t n_out, const uint32_t* in_off, const uint32_t* out_off,
+                       uint32_t nbuckets, uint32_t* src, size_t stride) {
+  uint32_t b = 0, ob = 0, oe = 0, ib = 0, ie = 0;
+  if (slot0 < n_out) {
+    // last bucket whose first output slot is <= slot0 (empty buckets share a start with their
+    // successor, so "last" is the one that really owns the slot)
+    uint32_t lo = 0, hi = nbuckets;
+    while (hi - lo > 1) {
+      uint32_t mid = (lo + hi) >> 1;
+      if (out_off[mid] <= slot0) lo = mid; else hi = mid;
+    }
+    b = lo;
+    ob = out_off[b]; oe = out_off[b + 1];
+    ib = in_off[b]; ie = in_off[b + 1];
+  }
+#pragma unroll 1
+  for (int k = 0; k < B; k++) {
+    uint32_t j = slot0 + (uint32_t)k;
+    uint32_t s = PAIR_NONE;
+    if (j < n_out) {
+      if (j >= oe) {
+        do { b++; ob = oe; oe = out_off[b + 1]; } while (j >= oe);
+        ib = in_off[b]; ie = in_off[b + 1];
+      }
+      s = ib + 2u * (j - ob);
+      if (s + 1 >= ie) s |= PAIR_SINGLE;
+    }
+    src[(size_t)k * stride] = s;
+  }
+}
+
+template <class F, bool L0>
+B381_DI F pair_load_x(uint32_t pos, const uint32_t* svals, const affine_t<F>* pts) {
+  return L0 ? pts[svals[pos] >> 1].x : pts[pos].x;
+}
+
+// Forward: pre[k*pstride] = product of the denominators before k; returns the product of all B.
+template <class F, int B, bool L0>
+B381_DI F pair_phase1(const uint32_t* src, size_t sstride, const uint32_t* svals, const affine_t<F>* pts, F* pre,
+                      size_t pstride) {
+  F acc = one<F>();
+#pragma unroll 4
+  for (int k = 0; k < B; k++) {
+    uint32_t s = src[(size_t)k * sstride];
+    pre[(size_t)k * pstride] = acc;
+    if (s & PAIR_SINGLE) continue;          // carried-over point or no slot: no denominator
+    F x1 = pair_load_x<F, L0>(s, svals, pts);
+    F x2 = pair_load_x<F, L0>(s + 1, svals, pts);
+    F d = sub(x2, x1);
+    if (is_zero(x1) || is_zero(x2) || is_zero(d)) {   // infinity operand, doubling or cancellation: rare
+      affine_t<F> p = pair_load<F, L0>(s, svals, pts);
+      affine_t<F> q = pair_load<F, L0>(s + 1, svals, pts);
+      pair_classify(p, q, d);
+    }
+    acc = mul(acc, d);
+  }
+  return acc;
+}
+
+// Backward: `inv_total` is the inverse of what phase1 returned; out points at the thread's first slot.
+template <class F, int B, bool L0>
+B381_DI void pair_phase2(F inv_total, const uint32_t* src, size_t sstride, const uint32_t* svals,
+                         const affine_t<F>* pts, const F* pre, size_t pstride, affine_t<F>* out) {
+  uint32_t s_next = src[(size_t)(B - 1) * sstride];
+#pragma unroll 1
+  for (int k = B - 1; k >= 0; k--) {
+    uint32_t s = s_next;
+    if (k) s_next = src[(size_t)(k - 1) * sstride];   // one hop of the src -> svals -> point chain ahead
+    if (s == PAIR_NONE) continue;
+    uint32_t p0 = s & ~PAIR_SINGLE;
+    affine_t<F> p = pair_load<F, L0>(p0, svals, pts);
+    if (s & PAIR_SINGLE) { out[k] = p; continue; }
+    affine_t<F> q = pair_load<F, L0>(p0 + 1, svals, pts);
+    F d;
+    int kind = pair_classify(p, q, d);
+    F dinv = mul(inv_total, pre[(size_t)k * pstride]);
+    if (k) inv_total = mul(inv_total, d);
+    out[k] = pair_finish(kind, p, q, dinv);
+  }
+}
+
+// In-place inversion of `count` field elements, element j of thread t at v[j*nthreads + t], m <= MAXM
+// elements per thread: prefix products, one inversion, unwind.
+template <class F, int MAXM>
+B381_DI void batch_invert_body(uint32_t t, uint32_t nthreads, uint32_t count, uint32_t m, F* v) {
+  if (t >= nthreads) return;
+  F pf[MAXM];
+  F acc = one<F>();
+#pragma unroll 1
+  for (uint32_t j = 0; j < m; j++) {
+    size_t idx = (size_t)j * nthreads + t;
+    pf[j] = acc;
+    if (idx < count) acc = mul(acc, v[idx]);
+  }
+  F inv_acc = inv_vartime(acc);
+#pragma unroll 1
+  for (int j = (int)m - 1; j >= 0; j--) {
+    size_t idx = (size_t)j * nthreads + t;
+    if (idx >= count) continue;
+    F x = v[idx];
+    v[idx] = mul(inv_acc, pf[j]);
+    inv_acc = mul(inv_acc, x);
+  }
+}
+
+// elements per thread of the batched inversion: as many as keep ~2 waves of threads busy, at most MAXM
+B381_HD uint32_t batch_invert_m(uint32_t count, uint32_t maxm) {
+  uint32_t m = count / (148u * 256u);
+  if (m < 4) m = 4;
+  if (m > maxm) m = maxm;
+  return m;
+}
+
+}  // namespace b381

@@ -1,5 +1,5 @@
 // Per-thread bodies of the Pippenger MSM pipeline (G1 and G2), written so that each CUDA
-// kernel in msm.cu is `body(global_thread_id, ...)`.  The same bodies are driven by a serial
+// kernel in msm_impl.cuh is `body(global_thread_id, ...)`.  The same bodies are driven by a serial
 // loop in tests/host/msm_host_sim.cpp (CPU-only CI), which is how the pipeline logic is
 // checked without a GPU.
 //
@@ -10,6 +10,8 @@
 //                                                           [ref sorts all 32 bits, :768-778]
 //   3 offsets     bucket boundaries straight from the sorted keys (no histogram, no atomics)
 //                                                           [ref: histogram + scan, :224-256,:748-758]
+//   3b pre-reduce affine pairwise levels with CTA-wide batched inversion (msm_batch.cuh): each level
+//                 halves every bucket at 6 Fq products per removed point      [no reference counterpart]
 //   4 tasks       every bucket is cut into ceil(size/K) equal tasks so one thread never owns more
 //                 than K insertions, whatever the scalar distribution
 //                                                           [ref: 1 thread or 8/16 threads per bucket]
@@ -23,6 +25,7 @@
 #pragma once
 #include "curve.cuh"
 #include "fq_lazy.cuh"
+#include "msm_batch.cuh"
 
 namespace b381 {
 
@@ -51,6 +54,17 @@ B381_HD msm_shape make_msm_shape(uint32_t n, uint32_t c, uint32_t bits, uint32_t
 }
 
 B381_HD uint32_t ceil_div_u32(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
+
+// A bucket is cut into at most this many tasks, however large it is (all scalars equal puts every point
+// of a window into ONE bucket): its partials are then summed by one warp (32 per lane + a shuffle tree,
+// msm_tail.cu) instead of a serial chain of thousands of additions.
+constexpr uint32_t kMaxTasksPerBucket = 1024;
+// buckets with more partials than this are left to the warp-per-bucket finalize kernel
+constexpr uint32_t kFinalizeSerialMax = 8;
+B381_HD uint32_t msm_tasks_of(uint32_t size, uint32_t K) {
+  uint32_t nt = ceil_div_u32(size, K);
+  return nt > kMaxTasksPerBucket ? kMaxTasksPerBucket : nt;
+}
 
 // ---------------------------------------------------------------- 1 digits
 // Signed-digit recoding with the same digit set as the reference
@@ -106,14 +120,14 @@ B381_DI void msm_task_count_body(uint32_t b, const uint32_t* offsets, uint32_t n
                                  uint32_t* counts) {
   if (b >= nbuckets) return;
   uint32_t sz = offsets[b + 1] - offsets[b];
-  counts[b] = ceil_div_u32(sz, K);
+  counts[b] = msm_tasks_of(sz, K);
 }
 
 B381_DI void msm_build_tasks_body(uint32_t b, const uint32_t* offsets, const uint32_t* task_start,
                                   uint32_t nbuckets, uint32_t K, uint2* tasks) {
   if (b >= nbuckets) return;
   uint32_t beg = offsets[b], sz = offsets[b + 1] - beg;
-  uint32_t nt = ceil_div_u32(sz, K);
+  uint32_t nt = msm_tasks_of(sz, K);
   uint32_t t0 = task_start[b];
   // equal split: first (sz % nt) tasks get one extra element
   uint32_t base = nt ? sz / nt : 0, rem = nt ? sz % nt : 0, pos = beg;
@@ -134,7 +148,8 @@ B381_DI void msm_task_key_body(uint32_t t, uint32_t max_tasks, uint32_t ntasks, 
   uint32_t key = K + 1;
   if (t < ntasks) {
     uint2 tk = tasks[t];
-    key = K - (tk.y - tk.x);
+    uint32_t len = tk.y - tk.x;
+    key = len < K ? K - len : 0u;        // capped buckets have tasks longer than K: visit them first
   }
   keys[t] = key;
   ids[t] = t;
@@ -149,7 +164,7 @@ B381_DI void msm_accumulate_body(uint32_t t, uint32_t ntasks, const uint2* tasks
   uint2 tk = tasks[t];
   xyzz_t<F> acc = xyzz_identity<F>();
   for (uint32_t j = tk.x; j < tk.y; j++) {
-    uint32_t v = sorted_vals[j];
+    uint32_t v = sorted_vals ? sorted_vals[j] : (j << 1);   // nullptr: `bases` is a pre-reduced level (msm_batch.cuh)
     affine_t<F> p = bases[v >> 1];
     if (is_inf(p)) continue;            // (0,0) bases are legal and contribute nothing
     if (v & 1) p.y = neg(p.y);
@@ -183,9 +198,11 @@ B381_DI void msm_accumulate_lazy_body(uint32_t t, uint32_t ntasks, const uint2* 
 // ---------------------------------------------------------------- 6 finalize
 template <class F>
 B381_DI void msm_finalize_body(uint32_t b, uint32_t nbuckets, const uint32_t* task_start,
-                               const uint32_t* counts, const xyzz_t<F>* partial, xyzz_t<F>* buckets) {
+                               const uint32_t* counts, const xyzz_t<F>* partial, xyzz_t<F>* buckets,
+                               uint32_t serial_max = 0xFFFFFFFFu) {
   if (b >= nbuckets) return;
   uint32_t t0 = task_start[b], nt = counts[b];
+  if (nt > serial_max) return;            // a warp does this bucket (k_msm_finalize_heavy)
   xyzz_t<F> acc = xyzz_identity<F>();
   if (nt) acc = partial[t0];
   for (uint32_t t = 1; t < nt; t++) xyzz_add(acc, partial[t0 + t]);

@@ -1,4 +1,7 @@
-// Pippenger MSM for BLS12-381 G1 and G2 on sm_100a: kernels + host driver + C ABI.
+#pragma once
+// Pippenger MSM for BLS12-381 G1 and G2 on sm_100a: kernels + host driver, templated on the coordinate
+// field.  Instantiated by msm_g1.cu (Fq) and msm_g2.cu (Fq2) -- two translation units so the two
+// groups compile in parallel; the C ABI lives there.
 // Kernel bodies live in msm_core.cuh (host-testable); pipeline description there.
 //
 // Replaces: msm::msm_cuda<S,A,P> (bls12-381/src/curve/msm_kernels.cu:603-903) and the ICICLE
@@ -16,29 +19,29 @@
 namespace b381 {
 
 // ------------------------------------------------------------------ kernels
-__global__ void k_msm_digits(const fr_t* scalars, bool mont, msm_shape sh, uint32_t* keys, uint32_t* vals) {
+static __global__ void k_msm_digits(const fr_t* scalars, bool mont, msm_shape sh, uint32_t* keys, uint32_t* vals) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   msm_digits_body(i, scalars, mont, sh, keys, vals);
 }
 
-__global__ void k_msm_offsets(const uint32_t* sorted_keys, size_t total, uint32_t nbuckets, uint32_t* offsets) {
+static __global__ void k_msm_offsets(const uint32_t* sorted_keys, size_t total, uint32_t nbuckets, uint32_t* offsets) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   msm_offsets_body(j, sorted_keys, total, nbuckets, offsets);
 }
 
-__global__ void k_msm_task_count(const uint32_t* offsets, uint32_t nbuckets, uint32_t K, uint32_t* counts) {
+static __global__ void k_msm_task_count(const uint32_t* offsets, uint32_t nbuckets, uint32_t K, uint32_t* counts) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == nbuckets) counts[b] = 0;  // sentinel so the exclusive scan yields the task total
   msm_task_count_body(b, offsets, nbuckets, K, counts);
 }
 
-__global__ void k_msm_build_tasks(const uint32_t* offsets, const uint32_t* task_start, uint32_t nbuckets,
+static __global__ void k_msm_build_tasks(const uint32_t* offsets, const uint32_t* task_start, uint32_t nbuckets,
                                   uint32_t K, uint2* tasks) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   msm_build_tasks_body(b, offsets, task_start, nbuckets, K, tasks);
 }
 
-__global__ void k_msm_task_keys(uint32_t max_tasks, const uint32_t* ntasks_dev, const uint2* tasks, uint32_t K,
+static __global__ void k_msm_task_keys(uint32_t max_tasks, const uint32_t* ntasks_dev, const uint2* tasks, uint32_t K,
                                 uint32_t* keys, uint32_t* ids) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   msm_task_key_body(t, max_tasks, *ntasks_dev, tasks, K, keys, ids);
@@ -52,14 +55,14 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* nt
   msm_accumulate_body<F>(t, *ntasks_dev, tasks, sorted_vals, bases, partial, order);
 }
 
-__global__ void __launch_bounds__(128, 3) k_msm_accumulate_lazy(const uint32_t* ntasks_dev, const uint2* tasks,
+static __global__ void __launch_bounds__(128, 3) k_msm_accumulate_lazy(const uint32_t* ntasks_dev, const uint2* tasks,
                                                                const uint32_t* sorted_vals, const g1_affine* bases,
                                                                g1_xyzz* partial, const uint32_t* order) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   msm_accumulate_lazy_body(t, *ntasks_dev, tasks, sorted_vals, bases, partial, order);
 }
 template <class F> static bool launch_lazy(unsigned, cudaStream_t, const uint32_t*, const uint2*, const uint32_t*, const affine_t<F>*, xyzz_t<F>*, const uint32_t*) { return false; }
-template <> bool launch_lazy<fq_t>(unsigned g, cudaStream_t st, const uint32_t* nt, const uint2* tasks, const uint32_t* sv,
+template <> inline bool launch_lazy<fq_t>(unsigned g, cudaStream_t st, const uint32_t* nt, const uint2* tasks, const uint32_t* sv,
                                    const g1_affine* bases, g1_xyzz* partial, const uint32_t* order) {
   const char* e = getenv("B381_ACC_LAZY");
   if (!e || e[0] != '1') return false;
@@ -67,13 +70,26 @@ template <> bool launch_lazy<fq_t>(unsigned g, cudaStream_t st, const uint32_t* 
   return true;
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_finalize(uint32_t nbuckets, const uint32_t* task_start,
-                                                      const uint32_t* counts, const xyzz_t<F>* partial,
-                                                      xyzz_t<F>* buckets) {
+// ---- affine pre-reduction (msm_batch.cuh): three kernels per level, no barriers ----------------
+static __global__ void k_msm_half_counts(const uint32_t* offsets, uint32_t nbuckets, uint32_t* counts) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_finalize_body<F>(b, nbuckets, task_start, counts, partial, buckets);
+  msm_half_counts_body(b, offsets, nbuckets, counts);
 }
+
+// The three kernels of a level live in msm_pair.cu (their own translation unit: seconds to compile).
+// Launches k_msm_pair_fwd, k_msm_invert_totals, k_msm_pair_bwd for one level; `grid` CTAs of PR_TPB threads,
+// nt = grid * PR_TPB = stride of the slot-major scratch arrays.
+// msm_pair_levels: how many levels pay for `total` sorted entries at a mean bucket load of `avg`.
+int msm_pair_levels(double avg, size_t total);
+template <class F>
+void launch_pair_level(bool level0, const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets,
+                       const uint32_t* svals, const affine_t<F>* pts, unsigned grid, uint32_t* srcg, F* preg, F* tot,
+                       affine_t<F>* out, cudaStream_t st);
+
+// bucket = sum of its task partials (thread per bucket, warp per heavy bucket): msm_tail.cu
+template <class F>
+void launch_msm_finalize(uint32_t nbuckets, const uint32_t* task_start, const uint32_t* counts, const xyzz_t<F>* partial,
+                         xyzz_t<F>* buckets, cudaStream_t st);
 
 template <class F>
 __global__ void __launch_bounds__(64) k_msm_segment(uint32_t W, uint32_t B, uint32_t L, const xyzz_t<F>* buckets,
@@ -88,10 +104,9 @@ __global__ void __launch_bounds__(64) k_msm_tree(uint32_t groups, uint32_t strid
   msm_tree_body<F>(g, groups, stride, half, a);
 }
 
+// Horner over the window sums with four lanes sharing each doubling: msm_tail.cu
 template <class F>
-__global__ void k_msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c, xyzz_t<F>* out) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) *out = msm_combine<F>(wsum, stride, W, c);
-}
+void launch_msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c, xyzz_t<F>* out, cudaStream_t st);
 
 template <class F>
 __global__ void k_msm_set_identity(xyzz_t<F>* out) {
@@ -131,8 +146,9 @@ __global__ void __launch_bounds__(64) k_precompute_bases(const affine_t<F>* in, 
 }
 
 // ------------------------------------------------------------------ host driver
-static thread_local float g_last_timings[8];
-static thread_local int g_last_timings_n = 0;
+inline thread_local float g_last_timings[12];
+inline thread_local int g_last_timings_n = 0;
+inline thread_local int g_last_info[4] = {0, 0, 0, 0};   // window bits, windows, affine levels, own kernel launches
 
 struct PhaseTimer {
   bool on;
@@ -153,7 +169,7 @@ struct PhaseTimer {
     if (!on || ev.empty()) return;
     cudaEventSynchronize(ev.back());
     g_last_timings_n = 0;
-    for (size_t i = 1; i < ev.size() && g_last_timings_n < 8; i++)
+    for (size_t i = 1; i < ev.size() && g_last_timings_n < 12; i++)
       cudaEventElapsedTime(&g_last_timings[g_last_timings_n++], ev[i - 1], ev[i]);
     for (auto e : ev) cudaEventDestroy(e);
     ev.clear();
@@ -179,6 +195,10 @@ static uint32_t pick_window(uint32_t n, uint32_t bits, uint32_t factor) {
   for (uint32_t c = 4; c <= 16; c++) {
     uint32_t W = (bits + 1 + c - 1) / c;
     uint32_t Wf = (W + factor - 1) / factor;
+    // the top window holds only t = bits+1 - (W-1)c bits: with t << c its 2^t buckets each take n/2^t
+    // points (n = 2^16, c = 11: five buckets of 16384) -- keep it within 8x of the other windows' load
+    uint32_t t = bits + 1 - (W - 1) * c;
+    if (t + 4 < c) continue;
     double cost = (double)W * 10.0 * n + (double)Wf * 72.0 * (double)(1u << (c - 1));
     if (cost < best) { best = cost; bc = c; }
   }
@@ -199,7 +219,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   if (c > 24) c = 24;
   const msm_shape sh = make_msm_shape(n, c, bits, factor);
   if ((uint64_t)n * factor >= (1ull << 31)) return cudaErrorInvalidValue;
-  const size_t total = (size_t)n * sh.W;
+  size_t total = (size_t)n * sh.W;
   if (total >= (1ull << 31)) return cudaErrorInvalidValue;
 
   // -- 1 digits
@@ -224,14 +244,73 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   const uint32_t* svals = dv.Current();
   tm.mark();
 
-  // -- 3 offsets, 4 tasks
+  // -- 3 offsets
   uint32_t *offsets, *counts, *task_start;
   B381_CUDA_TRY(sc.alloc(&offsets, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(sc.alloc(&counts, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(sc.alloc(&task_start, (size_t)sh.nbuckets + 1));
   k_msm_offsets<<<grid_for(total + 1, 256), 256, 0, st>>>(skeys, total, sh.nbuckets, offsets);
+  tm.mark();
+
+  // -- 3b affine pre-reduction levels (msm_batch.cuh): each halves every bucket
+  const affine_t<F>* acc_pts = d_bases;
+  const uint32_t* acc_vals = svals;
+  int n_levels = 0;
+  double avg = (double)n * sh.W / (double)sh.nbuckets;   // mean bucket load seen by the accumulate kernel
+  {
+    // a level pays once there are enough pairs to fill the GPU and buckets are still long
+    int levels = 0;
+    {
+      levels = msm_pair_levels(avg, total);
+      const char* e = getenv("B381_MSM_LEVELS");
+      if (e && e[0]) levels = atoi(e);
+      if (levels > 16) levels = 16;
+    }
+    size_t max_in = total;
+    const uint32_t* in_off = offsets;
+    affine_t<F>* buf[2] = {nullptr, nullptr};
+    constexpr int PB = pair_batch<F>::B;
+    uint32_t* srcg = nullptr;
+    F *preg = nullptr, *tot = nullptr;
+    for (int l = 0; l < levels; l++) {
+      const size_t max_out = (max_in + sh.nbuckets) / 2 + 1;
+      uint32_t *half, *out_off;
+      B381_CUDA_TRY(sc.alloc(&half, (size_t)sh.nbuckets + 1));
+      B381_CUDA_TRY(sc.alloc(&out_off, (size_t)sh.nbuckets + 1));
+      k_msm_half_counts<<<grid_for((size_t)sh.nbuckets + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, half);
+      size_t sb = 0;
+      B381_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, sb, half, out_off, (int)sh.nbuckets + 1, st));
+      uint8_t* stmp = nullptr;
+      B381_CUDA_TRY(sc.alloc(&stmp, sb));
+      B381_CUDA_TRY(cub::DeviceScan::ExclusiveSum(stmp, sb, half, out_off, (int)sh.nbuckets + 1, st));
+      const unsigned g = grid_for(max_out, (size_t)PR_TPB * PB);
+      const uint32_t nt = g * PR_TPB;
+      if (!buf[l & 1]) B381_CUDA_TRY(sc.alloc(&buf[l & 1], (size_t)nt * PB));   // ping-pong: sizes only shrink
+      if (!srcg) {                                                               // level 0 is the largest
+        B381_CUDA_TRY(sc.alloc(&srcg, (size_t)nt * PB));
+        B381_CUDA_TRY(sc.alloc(&preg, (size_t)nt * PB));
+        B381_CUDA_TRY(sc.alloc(&tot, (size_t)nt));
+      }
+      launch_pair_level<F>(l == 0, in_off, out_off, sh.nbuckets, l == 0 ? svals : nullptr,
+                           l == 0 ? d_bases : buf[(l - 1) & 1], g, srcg, preg, tot, buf[l & 1], st);
+      acc_pts = buf[l & 1];
+      acc_vals = nullptr;
+      in_off = out_off;
+      max_in = max_out;
+      avg *= 0.5;
+    }
+    n_levels = levels;
+    if (levels) {
+      // the task builder and the finalize step read bucket boundaries from `offsets`
+      B381_CUDA_TRY(cudaMemcpyAsync(offsets, in_off, sizeof(uint32_t) * ((size_t)sh.nbuckets + 1), cudaMemcpyDeviceToDevice, st));
+      total = max_in;
+    }
+  }
+  tm.mark();
+
+  // -- 4 tasks
   // task length bound: mean bucket load + 4 sigma (Poisson), so a uniform input is one task per bucket
-  double avg = (double)n / (double)sh.B;
+  if (avg < 1.0) avg = 1.0;
   uint32_t K = (uint32_t)(avg + 4.0 * sqrt(avg) + 8.0);
   {
     const char* e = getenv("B381_MSM_K");
@@ -269,7 +348,6 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
       order = bi.Current();
     }
   }
-  tm.mark();
 
   // -- 5 accumulate
   xyzz_t<F>*partial, *buckets;
@@ -280,14 +358,14 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
     const char* e = getenv("B381_ACC_MINB");
     if (e) variant = atoi(e);
     const unsigned g = grid_for(max_tasks, 128);
-    if (launch_lazy<F>(g, st, task_start + sh.nbuckets, tasks, svals, d_bases, partial, order)) {
-    } else if (variant == 3) k_msm_accumulate<F, 3><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial, order);
-    else if (variant == 4) k_msm_accumulate<F, 4><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial, order);
-    else k_msm_accumulate<F, 1><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, svals, d_bases, partial, order);
+    if (acc_vals && launch_lazy<F>(g, st, task_start + sh.nbuckets, tasks, svals, d_bases, partial, order)) {
+    } else if (variant == 3) k_msm_accumulate<F, 3><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, acc_vals, acc_pts, partial, order);
+    else if (variant == 4) k_msm_accumulate<F, 4><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, acc_vals, acc_pts, partial, order);
+    else k_msm_accumulate<F, 1><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, acc_vals, acc_pts, partial, order);
   }
   tm.mark();
   // -- 6 finalize
-  k_msm_finalize<F><<<grid_for(sh.nbuckets, 128), 128, 0, st>>>(sh.nbuckets, task_start, counts, partial, buckets);
+  launch_msm_finalize<F>(sh.nbuckets, task_start, counts, partial, buckets, st);
   tm.mark();
 
   // -- 7 segments, 8 tree
@@ -305,8 +383,16 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
     k_msm_tree<F><<<grid_for((size_t)sh.Wf * half, 64), 64, 0, st>>>(sh.Wf, segs, half, seg);
   tm.mark();
   // -- 9 combine
-  k_msm_combine<F><<<1, 1, 0, st>>>(seg, segs, sh.Wf, sh.c, d_out);
+  launch_msm_combine<F>(seg, segs, sh.Wf, sh.c, d_out, st);
   tm.mark();
+  {
+    int tree = 0;
+    for (uint32_t half = segs / 2; half >= 1; half >>= 1) tree++;
+    // digits, offsets | 4 per level (+ the offsets copy is a memcpy) | task_count, build_tasks, task_keys,
+    // accumulate, finalize | segment, tree levels, combine
+    g_last_info[0] = (int)sh.c; g_last_info[1] = (int)sh.W; g_last_info[2] = n_levels;
+    g_last_info[3] = 2 + 4 * n_levels + 6 + 1 + tree + 1;
+  }
   B381_CUDA_TRY(cudaGetLastError());
   tm.finish();
   return cudaSuccess;
@@ -438,73 +524,3 @@ static int combine_entry(const void* parts, int count, void* stream, bool on_dev
 
 }  // namespace b381
 
-using namespace b381;
-
-static_assert(sizeof(b381_g1_affine) == sizeof(g1_affine) && sizeof(b381_g2_affine) == sizeof(g2_affine), "layout");
-static_assert(sizeof(b381_g1_projective) == sizeof(g1_jac) && sizeof(b381_g2_projective) == sizeof(g2_jac), "layout");
-static_assert(sizeof(b381_fr) == sizeof(fr_t), "layout");
-
-extern "C" {
-
-int b381_g1_msm(const b381_fr* s, const b381_g1_affine* p, int n, const b381_msm_config* cfg, b381_g1_projective* r) {
-  return msm_entry<fq_t>((const fr_t*)s, (const g1_affine*)p, n, cfg, r, ResultKind::IcicleStd);
-}
-int b381_g2_msm(const b381_fr* s, const b381_g2_affine* p, int n, const b381_msm_config* cfg, b381_g2_projective* r) {
-  return msm_entry<fq2_t>((const fr_t*)s, (const g2_affine*)p, n, cfg, r, ResultKind::IcicleStd);
-}
-// The reference's flat entry points call msm::msm_cuda directly, which never reads the Montgomery
-// flags: points are taken as Montgomery, scalars as integers (icicle_curve_api.cu:679-706,
-// msm_kernels.cu:603-903).  Same contract here, whatever the flags say.
-static b381_msm_config flat_cfg(const b381_msm_config* cfg) {
-  b381_msm_config c = *cfg;
-  c.are_points_montgomery_form = true;
-  c.are_scalars_montgomery_form = false;
-  c.batch_size = 1;
-  c.precompute_factor = 1;
-  return c;
-}
-int bls12_381_g1_msm_cuda(const b381_fr* s, const b381_g1_affine* p, int n, const b381_msm_config* cfg,
-                          b381_g1_projective* r) {
-  if (!cfg) return B381_INVALID_POINTER;
-  b381_msm_config c = flat_cfg(cfg);
-  return msm_entry<fq_t>((const fr_t*)s, (const g1_affine*)p, n, &c, r, ResultKind::JacobianMont);
-}
-int bls12_381_g2_msm_cuda(const b381_fr* s, const b381_g2_affine* p, int n, const b381_msm_config* cfg,
-                          b381_g2_projective* r) {
-  if (!cfg) return B381_INVALID_POINTER;
-  b381_msm_config c = flat_cfg(cfg);
-  return msm_entry<fq2_t>((const fr_t*)s, (const g2_affine*)p, n, &c, r, ResultKind::JacobianMont);
-}
-int b381_g1_msm_partial(const b381_fr* s, const b381_g1_affine* p, int n, const b381_msm_config* cfg, void* out) {
-  return msm_entry<fq_t>((const fr_t*)s, (const g1_affine*)p, n, cfg, out, ResultKind::PartialXyzz);
-}
-int b381_g2_msm_partial(const b381_fr* s, const b381_g2_affine* p, int n, const b381_msm_config* cfg, void* out) {
-  return msm_entry<fq2_t>((const fr_t*)s, (const g2_affine*)p, n, cfg, out, ResultKind::PartialXyzz);
-}
-int b381_g1_msm_combine(const void* parts, int count, void* stream, bool on_device, b381_g1_projective* r) {
-  return combine_entry<fq_t>(parts, count, stream, on_device, r);
-}
-int b381_g2_msm_combine(const void* parts, int count, void* stream, bool on_device, b381_g2_projective* r) {
-  return combine_entry<fq2_t>(parts, count, stream, on_device, r);
-}
-int b381_g1_msm_precompute_bases(const b381_g1_affine* in, int n, const b381_msm_config* cfg, b381_g1_affine* out) {
-  return precompute_entry<fq_t>((const g1_affine*)in, n, cfg, (g1_affine*)out);
-}
-int b381_g2_msm_precompute_bases(const b381_g2_affine* in, int n, const b381_msm_config* cfg, b381_g2_affine* out) {
-  return precompute_entry<fq2_t>((const g2_affine*)in, n, cfg, (g2_affine*)out);
-}
-int b381_msm_last_timings(float* out, int cap) {
-  int k = g_last_timings_n < cap ? g_last_timings_n : cap;
-  for (int i = 0; i < k; i++) out[i] = g_last_timings[i];
-  return k;
-}
-b381_msm_config b381_default_msm_config(void) {
-  b381_msm_config c;
-  memset(&c, 0, sizeof(c));
-  c.precompute_factor = 1;
-  c.batch_size = 1;
-  c.are_points_shared_in_batch = true;
-  return c;
-}
-
-}  // extern "C"

@@ -1,0 +1,82 @@
+// Affine bucket pre-reduction: the three kernels of one level (bodies in msm_batch.cuh) for G1 (Fq) and
+// G2 (Fq2), and their launcher.  Own translation unit so that tuning them does not recompile the rest of
+// the MSM.
+#include <cstdlib>
+
+#include "common.cuh"
+#include "msm_batch.cuh"
+
+namespace b381 {
+
+// thread t owns output slots [t*B, t*B + B); nt = threads in the grid = stride of the slot-major scratch
+template <class F, int B, bool L0>
+__global__ void __launch_bounds__(PR_TPB, 4) k_msm_pair_fwd(const uint32_t* in_off, const uint32_t* out_off,
+                                                            uint32_t nbuckets, const uint32_t* svals,
+                                                            const affine_t<F>* pts, uint32_t nt, uint32_t* srcg,
+                                                            F* preg, F* tot) {
+  const uint32_t n_out = out_off[nbuckets];
+  const uint32_t t = blockIdx.x * PR_TPB + threadIdx.x;
+  if ((uint64_t)t * B >= n_out) return;
+  pair_walk<B>(t * B, n_out, in_off, out_off, nbuckets, srcg + t, nt);
+  tot[t] = pair_phase1<F, B, L0>(srcg + t, nt, svals, pts, preg + t, nt);
+}
+
+// in-place inversion of the ceil(n_out / B) thread totals, up to M per thread
+template <class F, int B, int M>
+__global__ void __launch_bounds__(128) k_msm_invert_totals(const uint32_t* out_off, uint32_t nbuckets, F* tot) {
+  const uint32_t n_out = out_off[nbuckets];
+  const uint32_t count = (n_out + B - 1) / B;
+  const uint32_t m = batch_invert_m(count, M);
+  const uint32_t nthreads = (count + m - 1) / m;
+  batch_invert_body<F, M>(blockIdx.x * blockDim.x + threadIdx.x, nthreads, count, m, tot);
+}
+
+template <class F, int B, bool L0, int MINB>
+__global__ void __launch_bounds__(PR_TPB, MINB) k_msm_pair_bwd(const uint32_t* out_off, uint32_t nbuckets,
+                                                               const uint32_t* svals, const affine_t<F>* pts,
+                                                               uint32_t nt, const uint32_t* srcg, const F* preg,
+                                                               const F* tot, affine_t<F>* out) {
+  const uint32_t n_out = out_off[nbuckets];
+  const uint32_t t = blockIdx.x * PR_TPB + threadIdx.x;
+  if ((uint64_t)t * B >= n_out) return;
+  pair_phase2<F, B, L0>(tot[t], srcg + t, nt, svals, pts, preg + t, nt, out + (size_t)t * B);
+}
+
+template <class F, bool L0>
+static void launch_level(const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets, const uint32_t* svals,
+                         const affine_t<F>* pts, unsigned g, uint32_t* srcg, F* preg, F* tot, affine_t<F>* out,
+                         cudaStream_t st) {
+  constexpr int PB = pair_batch<F>::B, PM = pair_batch<F>::M;
+  const uint32_t nt = g * PR_TPB;
+  const unsigned gi = (unsigned)((((size_t)nt + 3) / 4 + 127) / 128);   // enough for the smallest per-thread batch (4)
+  static const int minb = [] { const char* e = getenv("B381_BWD_MINB"); return e ? atoi(e) : 4; }();
+  k_msm_pair_fwd<F, PB, L0><<<g, PR_TPB, 0, st>>>(in_off, out_off, nbuckets, svals, pts, nt, srcg, preg, tot);
+  k_msm_invert_totals<F, PB, PM><<<gi, 128, 0, st>>>(out_off, nbuckets, tot);
+  if (minb == 5) k_msm_pair_bwd<F, PB, L0, 5><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
+  else if (minb == 6) k_msm_pair_bwd<F, PB, L0, 6><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
+  else k_msm_pair_bwd<F, PB, L0, 4><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
+}
+
+// A level pays once there are enough pairs to fill the GPU (each level has ~0.25 ms of fixed latency: three
+// launches and one thread-serial inversion) and buckets are still long.  Measured on B200: 2^20 points -> 2
+// levels, 2^22 -> 4, 2^24 -> 6 (gpurun sweep, profiles/r01_msm_levels_sweep.txt).
+int msm_pair_levels(double avg, size_t total) {
+  int levels = 0;
+  while (levels < 8 && avg >= 8.0 && total / 2 >= ((size_t)1 << 22)) { levels++; avg *= 0.5; total /= 2; }
+  return levels;
+}
+
+template <class F>
+void launch_pair_level(bool level0, const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets,
+                       const uint32_t* svals, const affine_t<F>* pts, unsigned grid, uint32_t* srcg, F* preg, F* tot,
+                       affine_t<F>* out, cudaStream_t st) {
+  if (level0) launch_level<F, true>(in_off, out_off, nbuckets, svals, pts, grid, srcg, preg, tot, out, st);
+  else launch_level<F, false>(in_off, out_off, nbuckets, nullptr, pts, grid, srcg, preg, tot, out, st);
+}
+
+template void launch_pair_level<fq_t>(bool, const uint32_t*, const uint32_t*, uint32_t, const uint32_t*, const affine_t<fq_t>*,
+                                      unsigned, uint32_t*, fq_t*, fq_t*, affine_t<fq_t>*, cudaStream_t);
+template void launch_pair_level<fq2_t>(bool, const uint32_t*, const uint32_t*, uint32_t, const uint32_t*, const affine_t<fq2_t>*,
+                                       unsigned, uint32_t*, fq2_t*, fq2_t*, affine_t<fq2_t>*, cudaStream_t);
+
+}  // namespace b381

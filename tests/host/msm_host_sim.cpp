@@ -1,7 +1,10 @@
 // CPU-only driver for the per-thread MSM bodies in csrc/msm_core.cuh (TEST INFRASTRUCTURE).
-// Runs exactly the kernel pipeline of csrc/msm.cu with a serial loop per "kernel" and
+// Runs exactly the kernel pipeline of csrc/msm_impl.cuh with a serial loop per "kernel" and
 // std::stable_sort in place of the device radix sort.  Usage:
-//   msm_host_sim <g1|g2> <n> <c> <K> <L> <scalars_mont 0|1> <infile> [factor]; prints result hex (std form)
+//   msm_host_sim <g1|g2> <n> <c> <K> <L> <scalars_mont 0|1> <infile> [factor] [levels]; prints result hex (std form)
+// levels > 0 runs that many affine pre-reduction levels (csrc/msm_batch.cuh) before the tasks, 3 output
+// slots per simulated thread; forward, batched inversion of the thread totals and backward run as the three
+// per-level kernels do.
 // infile = n*32 B scalars followed by n*(96|192) B Montgomery affine points.
 // With factor > 1 the bases are first expanded exactly like k_precompute_bases does.
 #include <algorithm>
@@ -14,7 +17,7 @@
 using namespace b381;
 
 template <class F>
-int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint32_t factor) {
+int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint32_t factor, uint32_t levels) {
   std::vector<fr_t> sc(n);
   std::vector<affine_t<F>> pts(n);
   if (fread(sc.data(), sizeof(fr_t), n, f) != n) return 2;
@@ -42,6 +45,40 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint
   for (size_t j = 0; j < total; j++) { sk[j] = keys[perm[j]]; sv[j] = vals[perm[j]]; }
   std::vector<uint32_t> offsets(sh.nbuckets + 1, 0xdeadbeef);
   for (size_t j = 0; j <= total; j++) msm_offsets_body(j, sk.data(), total, sh.nbuckets, offsets.data());
+  // affine pre-reduction levels
+  const uint32_t* cur_vals = sv.data();
+  std::vector<affine_t<F>> lvl_pts;
+  for (uint32_t l = 0; l < levels; l++) {
+    constexpr int PB = 3;
+    std::vector<uint32_t> half(sh.nbuckets + 1), next_off(sh.nbuckets + 1);
+    for (uint32_t b = 0; b <= sh.nbuckets; b++) msm_half_counts_body(b, offsets.data(), sh.nbuckets, half.data());
+    uint32_t run_sum = 0;
+    for (uint32_t b = 0; b <= sh.nbuckets; b++) { next_off[b] = run_sum; run_sum += half[b]; }
+    uint32_t n_out = next_off[sh.nbuckets];
+    std::vector<affine_t<F>> outp((size_t)n_out + PB);
+    const affine_t<F>* inp = l == 0 ? pts.data() : lvl_pts.data();
+    // the three kernels of a level, thread by thread, with the same slot-major global layout
+    uint32_t NT = (n_out + PB - 1) / PB + 2;
+    std::vector<uint32_t> srcg((size_t)NT * PB);
+    std::vector<F> preg((size_t)NT * PB), tot(NT);
+    for (uint32_t t = 0; t < NT; t++) {
+      pair_walk<PB>(t * PB, n_out, offsets.data(), next_off.data(), sh.nbuckets, srcg.data() + t, NT);
+      tot[t] = l == 0 ? pair_phase1<F, PB, true>(srcg.data() + t, NT, cur_vals, inp, preg.data() + t, NT)
+                      : pair_phase1<F, PB, false>(srcg.data() + t, NT, nullptr, inp, preg.data() + t, NT);
+    }
+    constexpr int M = 8;
+    uint32_t mm = 1 + l % M;
+    uint32_t T2 = (NT + mm - 1) / mm;
+    for (uint32_t t = 0; t < T2; t++) batch_invert_body<F, M>(t, T2, NT, mm, tot.data());
+    for (uint32_t t = 0; t < NT; t++) {
+      if ((size_t)t * PB >= n_out) continue;
+      if (l == 0) pair_phase2<F, PB, true>(tot[t], srcg.data() + t, NT, cur_vals, inp, preg.data() + t, NT, outp.data() + (size_t)t * PB);
+      else pair_phase2<F, PB, false>(tot[t], srcg.data() + t, NT, nullptr, inp, preg.data() + t, NT, outp.data() + (size_t)t * PB);
+    }
+    lvl_pts.swap(outp);
+    offsets.swap(next_off);
+  }
+  if (levels) { pts = lvl_pts; cur_vals = nullptr; }
   std::vector<uint32_t> counts(sh.nbuckets), tstart(sh.nbuckets);
   for (uint32_t b = 0; b < sh.nbuckets; b++) msm_task_count_body(b, offsets.data(), sh.nbuckets, K, counts.data());
   uint32_t ntasks = 0;
@@ -49,7 +86,7 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint
   std::vector<uint2> tasks(ntasks ? ntasks : 1);
   for (uint32_t b = 0; b < sh.nbuckets; b++) msm_build_tasks_body(b, offsets.data(), tstart.data(), sh.nbuckets, K, tasks.data());
   std::vector<xyzz_t<F>> partial(ntasks ? ntasks : 1), buckets(sh.nbuckets);
-  for (uint32_t t = 0; t < ntasks; t++) msm_accumulate_body<F>(t, ntasks, tasks.data(), sv.data(), pts.data(), partial.data());
+  for (uint32_t t = 0; t < ntasks; t++) msm_accumulate_body<F>(t, ntasks, tasks.data(), cur_vals, pts.data(), partial.data());
   for (uint32_t b = 0; b < sh.nbuckets; b++) msm_finalize_body<F>(b, sh.nbuckets, tstart.data(), counts.data(), partial.data(), buckets.data());
   if (L > sh.B) L = sh.B;
   uint32_t segs = sh.B / L;
@@ -73,7 +110,8 @@ int main(int argc, char** argv) {
   FILE* f = fopen(argv[7], "rb");
   if (!f) return 3;
   uint32_t factor = argc > 8 ? atoi(argv[8]) : 1;
-  int rc = g2 ? run<fq2_t>(n, c, K, L, mont, f, factor) : run<fq_t>(n, c, K, L, mont, f, factor);
+  uint32_t levels = argc > 9 ? atoi(argv[9]) : 0;
+  int rc = g2 ? run<fq2_t>(n, c, K, L, mont, f, factor, levels) : run<fq_t>(n, c, K, L, mont, f, factor, levels);
   fclose(f);
   return rc;
 }

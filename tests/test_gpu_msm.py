@@ -128,6 +128,75 @@ def test_edge_cases(cuda, b381, oracle):
     assert lib.b381_g1_msm(b381.ptr(sc), b381.ptr(bases), -1, C.byref(cfg), b381.ptr(np.zeros(18, dtype=np.uint64))) == 11
 
 
+@pytest.mark.parametrize("levels", [0, 1, 2, 5])
+def test_affine_prereduction_levels(cuda, b381, oracle, monkeypatch, levels):
+    """csrc/msm_batch.cuh forced on at small sizes: every bucket halved `levels` times by affine pair sums under
+    one CTA-wide batched inversion before the task/accumulate path; random inputs with long buckets, infinity
+    bases, zero scalars, identical bases (every pair a doubling), P/-P pairs (every pair cancels), and G2."""
+    monkeypatch.setenv("B381_MSM_LEVELS", str(levels))
+    n = 5000
+    bases = oracle.gen_series(1, [9, 1, 0, 0], [5, 0, 7, 0], n)
+    sc = oracle.random_fr(31 + levels, n)
+    sc[7] = 0
+    sc[8] = sc[9]
+    bases[11] = 0
+    bases[12] = 0
+    exp = oracle.msm(1, sc, bases).tobytes()
+    for c in (4, 7, 11):
+        assert raw_msm(b381, "g1", sc, bases, n, c=c).tobytes() == exp, c
+    g = oracle.generator(1)
+    m = 777
+    assert raw_msm(b381, "g1", fr_array([5] * m), np.tile(g, (m, 1)), m, c=5).tobytes() == \
+        P.g1_result_std_bytes(P.g1_mul(5 * m, P.G1_GEN))
+    assert raw_msm(b381, "g1", fr_array(list(range(1, m + 1))), np.tile(g, (m, 1)), m, c=6).tobytes() == \
+        P.g1_result_std_bytes(P.g1_mul(m * (m + 1) // 2, P.G1_GEN))
+    neg = np.frombuffer(P.g1_affine_mont_bytes(P.g1_neg(P.G1_GEN)), dtype=np.uint64)
+    pair = np.stack([g, neg] * 64)
+    assert raw_msm(b381, "g1", fr_array([12345] * 128), pair, 128, c=4).tobytes() == P.g1_result_std_bytes(None)
+    n2 = 600
+    bases2 = oracle.gen_series(2, [3, 0, 0, 1], [1, 2, 0, 0], n2)
+    sc2 = oracle.random_fr(77, n2)
+    sc2[5] = sc2[6]
+    bases2[6] = bases2[5]
+    assert raw_msm(b381, "g2", sc2, bases2, n2, c=5).tobytes() == oracle.msm(2, sc2, bases2).tobytes()
+
+
+@pytest.mark.parametrize("levels", ["", "0", "3"])
+def test_skewed_scalar_distributions(cuda, b381, oracle, monkeypatch, levels):
+    """All scalars equal (commitment to a constant vector; the reference's "sum of ones" identity,
+    test_msm_security.cu:410-505, at scale): every window has ONE bucket holding all n points.  The bucket is cut
+    into at most 1024 tasks and summed by the warp-per-bucket finalize kernel; with affine levels it is halved
+    level by level, balanced by output slot.  Checked through sum s (k0 + i d) G = s (n k0 + d n(n-1)/2) G."""
+    import torch
+    if levels:
+        monkeypatch.setenv("B381_MSM_LEVELS", levels)
+    n = 1 << 17
+    rng = P.SplitMix64(0x5EED)
+    k0, d, s = rng.fr(), rng.fr(), rng.fr()
+    bases = oracle.gen_series(1, P.to_limbs(k0, 4), P.to_limbs(d, 4), n)
+    d_bases = torch.from_numpy(bases.view(np.int64)).cuda()
+    tot = (n * k0 + d * (n * (n - 1) // 2)) % P.R_MOD
+    for val in (s, 1, P.R_MOD - 1):
+        sc = np.tile(np.array(P.to_limbs(val, 4), dtype=np.uint64), (n, 1))
+        d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+        got = raw_msm(b381, "g1", d_sc, d_bases, n, scalars_on_device=True, points_on_device=True)
+        assert got.tobytes() == P.g1_result_std_bytes(P.g1_mul(val * tot % P.R_MOD, P.G1_GEN)), val
+    # half the scalars zero, the rest one of two values
+    sc = np.zeros((n, 4), dtype=np.uint64)
+    sc[1::2] = np.array(P.to_limbs(s, 4), dtype=np.uint64)
+    sc[3::4] = np.array(P.to_limbs(7, 4), dtype=np.uint64)
+    idx = np.arange(n)
+    def dl(sel):
+        ii = [int(i) for i in idx[sel]]
+        return (len(ii) * k0 + d * sum(ii)) % P.R_MOD
+    m_s = np.zeros(n, dtype=bool); m_s[1::2] = True; m_s[3::4] = False
+    m_7 = np.zeros(n, dtype=bool); m_7[3::4] = True
+    exp = (s * dl(m_s) + 7 * dl(m_7)) % P.R_MOD
+    d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+    got = raw_msm(b381, "g1", d_sc, d_bases, n, scalars_on_device=True, points_on_device=True)
+    assert got.tobytes() == P.g1_result_std_bytes(P.g1_mul(exp, P.G1_GEN))
+
+
 def test_window_sizes_agree(cuda, b381, oracle):
     """the reference never compares window sizes; we do."""
     n = 4096

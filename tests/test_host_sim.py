@@ -28,7 +28,7 @@ def sims(tmp_path_factory):
     return bins
 
 
-def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1):
+def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1, levels=0):
     path = os.path.join(sims["dir"], "msm_in.bin")
     with open(path, "wb") as f:
         for s in scalars:
@@ -36,7 +36,7 @@ def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1):
         for pt in pts:
             f.write(P.g1_affine_mont_bytes(pt) if group == "g1" else P.g2_affine_mont_bytes(pt))
     r = subprocess.run([sims["msm_host_sim"], group, str(len(scalars)), str(c), str(K), str(L), str(int(mont)), path,
-                        str(factor)], capture_output=True, text=True, check=True)
+                        str(factor), str(levels)], capture_output=True, text=True, check=True)
     return bytes.fromhex(r.stdout.strip())
 
 
@@ -50,6 +50,37 @@ def test_msm_pipeline_g1(sims):
             sc[1], sc[2], sc[3], pts[4] = 0, 1, P.R_MOD - 1, None
         exp = P.g1_mul(sum(s * k for s, k, p in zip(sc, ks, pts) if p is not None) % P.R_MOD, P.G1_GEN)
         assert run_msm(sims, "g1", sc, pts, c, K, L) == P.g1_result_std_bytes(exp), (n, c)
+
+
+def test_msm_affine_prereduction_levels(sims):
+    """csrc/msm_batch.cuh: pairwise affine levels in front of the task/accumulate path, G1 and G2, including the
+    exceptional pairs (P+P, P-P, infinity operands, odd leftovers, empty buckets, slots past the end)."""
+    rng = P.SplitMix64(77)
+    for (n, c, K, L, levels) in [(1, 4, 2, 2, 1), (9, 3, 2, 2, 2), (64, 4, 3, 4, 1), (64, 4, 3, 4, 3), (150, 5, 4, 8, 2), (150, 3, 50, 2, 6)]:
+        ks = [rng.fr() for _ in range(n)]
+        pts = [P.g1_mul(k, P.G1_GEN) for k in ks]
+        sc = [rng.fr() for _ in range(n)]
+        if n > 4:
+            sc[1], sc[2], sc[3], pts[4] = 0, 1, P.R_MOD - 1, None
+        exp = P.g1_mul(sum(s * k for s, k, p in zip(sc, ks, pts) if p is not None) % P.R_MOD, P.G1_GEN)
+        assert run_msm(sims, "g1", sc, pts, c, K, L, levels=levels) == P.g1_result_std_bytes(exp), (n, c, levels)
+    for levels in (1, 2, 5):
+        # identical bases: every pair is a doubling; then P + (-P): every pair cancels; infinity operands
+        assert run_msm(sims, "g1", [5] * 40, [P.G1_GEN] * 40, 4, 3, 2, levels=levels) == P.g1_result_std_bytes(P.g1_mul(200, P.G1_GEN))
+        pts = [P.G1_GEN, P.g1_neg(P.G1_GEN)] * 10
+        assert run_msm(sims, "g1", [7] * 20, pts, 4, 3, 2, levels=levels) == P.g1_result_std_bytes(None)
+        pts = [P.G1_GEN, None, None, P.G1_GEN, None] * 4
+        assert run_msm(sims, "g1", [3] * 20, pts, 4, 3, 2, levels=levels) == P.g1_result_std_bytes(P.g1_mul(24, P.G1_GEN))
+    n = 14
+    ks = [rng.fr() for _ in range(n)]
+    sc = [rng.fr() for _ in range(n)]
+    sc[3] = sc[4] = sc[5]
+    ks[4] = ks[3]                         # equal points in one bucket -> Fq2 doubling
+    ks[5] = P.R_MOD - ks[3]               # and a cancellation
+    pts2 = [P.g2_mul(k, P.G2_GEN) for k in ks]
+    dl = sum(s * k for s, k in zip(sc, ks)) % P.R_MOD
+    for levels in (1, 3):
+        assert run_msm(sims, "g2", sc, pts2, 4, 3, 4, levels=levels) == P.g2_result_std_bytes(P.g2_mul(dl, P.G2_GEN))
 
 
 def test_msm_pipeline_exceptional_cases(sims):
