@@ -12,7 +12,7 @@
 // The reference has no counterpart: it accumulates in Jacobian coordinates with an add that also
 // evaluates a doubling every time (bls12-381/src/curve/msm_kernels.cu:269-366,
 // include/point.cuh:803-912).  The affine result of the MSM is representation independent, so
-// bit-exactness against the oracle is unaffected.
+// bit-exactness of the result is unaffected.
 //
 // One thread owns B consecutive output slots.  Three kernels per level, no barrier anywhere:
 //   k_msm_pair_fwd     walk the slots (slot -> input pair), denominators, running product; the exclusive
