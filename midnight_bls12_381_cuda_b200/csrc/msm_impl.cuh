@@ -86,23 +86,13 @@ void launch_pair_level(bool level0, const uint32_t* in_off, const uint32_t* out_
                        const uint32_t* svals, const affine_t<F>* pts, unsigned grid, uint32_t* srcg, F* preg, F* tot,
                        affine_t<F>* out, cudaStream_t st);
 
+// window sums from the buckets, four lanes per segment: msm_tail.cu
+template <class F>
+void launch_msm_bucket_reduce(uint32_t W, uint32_t B, uint32_t L, const xyzz_t<F>* buckets, xyzz_t<F>* seg, cudaStream_t st);
 // bucket = sum of its task partials (thread per bucket, warp per heavy bucket): msm_tail.cu
 template <class F>
 void launch_msm_finalize(uint32_t nbuckets, const uint32_t* task_start, const uint32_t* counts, const xyzz_t<F>* partial,
                          xyzz_t<F>* buckets, cudaStream_t st);
-
-template <class F>
-__global__ void __launch_bounds__(64) k_msm_segment(uint32_t W, uint32_t B, uint32_t L, const xyzz_t<F>* buckets,
-                                                    xyzz_t<F>* seg_out) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_segment_body<F>(g, W, B, L, buckets, seg_out);
-}
-
-template <class F>
-__global__ void __launch_bounds__(64) k_msm_tree(uint32_t groups, uint32_t stride, uint32_t half, xyzz_t<F>* a) {
-  uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_tree_body<F>(g, groups, stride, half, a);
-}
 
 // Horner over the window sums with four lanes sharing each doubling: msm_tail.cu
 template <class F>
@@ -378,9 +368,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   uint32_t segs = sh.B / L;
   xyzz_t<F>* seg;
   B381_CUDA_TRY(sc.alloc(&seg, (size_t)sh.Wf * segs));
-  k_msm_segment<F><<<grid_for((size_t)sh.Wf * segs, 64), 64, 0, st>>>(sh.Wf, sh.B, L, buckets, seg);
-  for (uint32_t half = segs / 2; half >= 1; half >>= 1)
-    k_msm_tree<F><<<grid_for((size_t)sh.Wf * half, 64), 64, 0, st>>>(sh.Wf, segs, half, seg);
+  launch_msm_bucket_reduce<F>(sh.Wf, sh.B, L, buckets, seg, st);
   tm.mark();
   // -- 9 combine
   launch_msm_combine<F>(seg, segs, sh.Wf, sh.c, d_out, st);

@@ -28,8 +28,7 @@ __device__ __forceinline__ F sel4(int role, const F& a0, const F& a1, const F& a
 
 // every lane holds the same point; lanes with (lane & 3) == role do the role's product of each level
 template <class F>
-__device__ __forceinline__ xyzz_t<F> xyzz_dbl_coop(const xyzz_t<F>& p, int role) {
-  if (is_inf(p)) return p;
+__device__ __forceinline__ xyzz_t<F> xyzz_dbl_coop_always(const xyzz_t<F>& p, int role) {
   const F u = dbl(p.y);
   F r = mul(sel4(role, u, p.x, u, u), sel4(role, u, p.x, u, u));
   const F v = shfl4(r, 0), xx = shfl4(r, 1);
@@ -44,6 +43,116 @@ __device__ __forceinline__ xyzz_t<F> xyzz_dbl_coop(const xyzz_t<F>& p, int role)
   o.zzz = shfl4(r, 2);
   return o;
 }
+// callers whose whole warp holds the same point (the combine kernel) may skip the identity
+template <class F>
+__device__ __forceinline__ xyzz_t<F> xyzz_dbl_coop(const xyzz_t<F>& p, int role) {
+  if (is_inf(p)) return p;
+  return xyzz_dbl_coop_always(p, role);
+}
+
+// ---- bucket reduction: window_sum[w] = sum_j (j+1) * bucket[w][j]  (msm_core.cuh: msm_segment_body /
+// msm_tree_body are the serial statements of the same sums, used by the CPU-only harness).  Here FOUR lanes
+// own a segment: the general XYZZ addition (add-2008-s, 12M+2S) has dependency depth 4
+//   U1,U2,S1,S2 | PP,RR,ZZ1*ZZ2,ZZZ1*ZZZ2 | PPP,Q,ZZ3 | R*(Q-X3),S1*PPP,ZZZ3
+// so a lane multiplies one operand pair per level and results travel by width-4 shuffles: the 2L dependent
+// additions of a segment cost 4 product latencies each instead of 14.  All lanes of a group hold the same
+// points, so the special cases (identity operands, P = +-Q) are resolved by selects after the common path
+// and every lane always executes the same shuffles.
+template <class F>
+__device__ __forceinline__ void xyzz_add_coop(xyzz_t<F>& acc, const xyzz_t<F>& q, int role) {
+  const bool q_inf = is_inf(q), a_inf = is_inf(acc);
+  F r = mul(sel4(role, acc.x, q.x, acc.y, q.y), sel4(role, q.zz, acc.zz, q.zzz, acc.zzz));
+  const F u1 = shfl4(r, 0), u2 = shfl4(r, 1), s1 = shfl4(r, 2), s2 = shfl4(r, 3);
+  const F p = sub(u2, u1), rr0 = sub(s2, s1);
+  r = mul(sel4(role, p, rr0, acc.zz, acc.zzz), sel4(role, p, rr0, q.zz, q.zzz));
+  const F pp = shfl4(r, 0), rr = shfl4(r, 1), z12 = shfl4(r, 2), z123 = shfl4(r, 3);
+  r = mul(sel4(role, p, u1, z12, z12), pp);
+  const F ppp = shfl4(r, 0), q1 = shfl4(r, 1), zz3 = shfl4(r, 2);
+  xyzz_t<F> o;
+  o.x = sub(sub(rr, ppp), dbl(q1));
+  r = mul(sel4(role, rr0, s1, z123, z123), sel4(role, sub(q1, o.x), ppp, ppp, ppp));
+  o.y = sub(shfl4(r, 0), shfl4(r, 1));
+  o.zz = zz3;
+  o.zzz = shfl4(r, 2);
+  if (q_inf) return;
+  if (a_inf) { acc = q; return; }
+  if (is_zero(p)) {                       // same x: doubling or cancellation (rare), serial formulas
+    if (is_zero(rr0)) acc = xyzz_dbl(acc);
+    else acc = xyzz_identity<F>();
+    return;
+  }
+  acc = o;
+}
+
+// k * p for k < 2^kbits, the products shared by the four lanes; all lanes of a group see the same k
+template <class F>
+__device__ __forceinline__ xyzz_t<F> xyzz_mul_small_coop(const xyzz_t<F>& p, uint32_t k, int kbits, int role) {
+  xyzz_t<F> r = xyzz_identity<F>();
+#pragma unroll 1
+  for (int i = kbits - 1; i >= 0; i--) {
+    // every group of the warp runs all kbits rounds so that the shuffles stay warp-uniform
+    xyzz_t<F> d = r;
+    {
+      // xyzz_dbl_coop returns early on the identity; run its shuffles unconditionally instead
+      const bool inf = is_inf(r);
+      xyzz_t<F> t = r;
+      if (inf) t = p;                    // any finite point keeps the arithmetic well defined
+      t = xyzz_dbl_coop_always(t, role);
+      if (!inf) d = t;
+    }
+    r = d;
+    xyzz_t<F> s = r;
+    xyzz_add_coop(s, p, role);
+    if ((k >> i) & 1) r = s;
+  }
+  return r;
+}
+
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_segment_coop(uint32_t W, uint32_t B, uint32_t L, const xyzz_t<F>* buckets,
+                                                          xyzz_t<F>* seg_out) {
+  const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const int role = threadIdx.x & 3;
+  const uint32_t segs = B / L;
+  const bool live = gid < W * segs;       // dead groups still run the shuffles (on segment 0)
+  const uint32_t g = live ? gid : 0;
+  const uint32_t w = g / segs, s = g % segs;
+  const xyzz_t<F>* bk = buckets + (size_t)w * B + (size_t)s * L;
+  xyzz_t<F> run = xyzz_identity<F>();
+  xyzz_t<F> tri = xyzz_identity<F>();
+#pragma unroll 1
+  for (int j = (int)L - 1; j >= 0; j--) {
+    xyzz_add_coop(run, bk[j], role);
+    xyzz_add_coop(tri, run, role);
+  }
+  xyzz_t<F> sh = xyzz_mul_small_coop(run, s * L, 32 - __clz((B - 1) | 1), role);
+  xyzz_add_coop(tri, sh, role);
+  if (live && role == 0) seg_out[g] = tri;
+}
+
+// in-place halving over groups: a[g*stride + t] += a[g*stride + t + half]
+template <class F>
+__global__ void __launch_bounds__(128) k_msm_tree_coop(uint32_t groups, uint32_t stride, uint32_t half, xyzz_t<F>* a) {
+  const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const int role = threadIdx.x & 3;
+  const bool live = gid < groups * half;
+  const uint32_t i = live ? gid : 0;
+  const uint32_t g = i / half, t = i % half;
+  xyzz_t<F> x = a[(size_t)g * stride + t];
+  xyzz_add_coop(x, a[(size_t)g * stride + t + half], role);
+  if (live && role == 0) a[(size_t)g * stride + t] = x;
+}
+
+// seg (W * B/L entries) is scratch; on return seg[w * (B/L)] = window sum w
+template <class F>
+void launch_msm_bucket_reduce(uint32_t W, uint32_t B, uint32_t L, const xyzz_t<F>* buckets, xyzz_t<F>* seg, cudaStream_t st) {
+  const uint32_t segs = B / L;
+  k_msm_segment_coop<F><<<grid_for((size_t)W * segs * 4, 128), 128, 0, st>>>(W, B, L, buckets, seg);
+  for (uint32_t half = segs / 2; half >= 1; half >>= 1)
+    k_msm_tree_coop<F><<<grid_for((size_t)W * half * 4, 128), 128, 0, st>>>(W, segs, half, seg);
+}
+template void launch_msm_bucket_reduce<fq_t>(uint32_t, uint32_t, uint32_t, const xyzz_t<fq_t>*, xyzz_t<fq_t>*, cudaStream_t);
+template void launch_msm_bucket_reduce<fq2_t>(uint32_t, uint32_t, uint32_t, const xyzz_t<fq2_t>*, xyzz_t<fq2_t>*, cudaStream_t);
 
 template <class F>
 __global__ void __launch_bounds__(32) k_msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c,
@@ -52,7 +161,7 @@ __global__ void __launch_bounds__(32) k_msm_combine(const xyzz_t<F>* wsum, uint3
   xyzz_t<F> r = xyzz_identity<F>();
   for (int w = (int)W - 1; w >= 0; w--) {
     for (uint32_t k = 0; k < c; k++) r = xyzz_dbl_coop(r, role);
-    xyzz_add(r, wsum[(size_t)w * stride]);
+    xyzz_add_coop(r, wsum[(size_t)w * stride], role);
   }
   if (threadIdx.x == 0) *out = r;
 }
