@@ -45,12 +45,28 @@ def _deps_mtime() -> float:
     return m
 
 
+def _deps_of(obj: str) -> list[str] | None:
+    """headers recorded by nvcc -MD for this object (None = no record yet)."""
+    dep = obj + ".d"
+    if not os.path.exists(dep):
+        return None
+    txt = open(dep).read().replace("\\\n", " ")
+    parts = txt.split(":", 1)
+    if len(parts) < 2:
+        return None
+    return [t for t in parts[1].split() if t.startswith(ROOT)]
+
+
 def _compile(src: str, hdr_mtime: float, verbose: bool) -> str:
     path = os.path.join(CSRC, src)
     obj = os.path.join(OBJ, src.replace("/", "_") + ".o")
-    if os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(path), hdr_mtime):
-        return obj
-    cmd = [NVCC] + NVCC_FLAGS + ["-c", path, "-o", obj]
+    if os.path.exists(obj):
+        deps = _deps_of(obj)
+        newest = hdr_mtime if deps is None else max(
+            [os.path.getmtime(d) if os.path.exists(d) else float("inf") for d in deps] + [0.0])
+        if os.path.getmtime(obj) > max(os.path.getmtime(path), newest):
+            return obj
+    cmd = [NVCC] + NVCC_FLAGS + ["-MD", "-MF", obj + ".d", "-c", path, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

@@ -71,17 +71,37 @@ def final_sub(b: Block, f: FieldSpec, r: list, outs: list[str], top=None):
 
 
 def reduce_step(b: Block, f: FieldSpec, E: list, O: list):
-    """E,O += m_i * modulus so that E[0] becomes 0; carries folded into O[n-1]."""
+    """E,O += m_i * modulus so that E[0] becomes 0; carries folded into O[n-1].
+
+    Fr has -r^-1 = -1 (mod 2^32) and its two low limbs are 1 and 0xffffffff, so for Fr
+        m_i = -E[0],   m_i * 1 = m_i,   m_i * 0xffffffff = E[0] + (m_i - [E[0] != 0]) * 2^32
+    and three of the nine multiplier instructions of a reduction row become adds on the ALU pipe
+    (the heavy pipe is what bounds the NTT: DESIGN.md section 3)."""
     n = f.n
-    mi = b.op3("mul.lo.u32", E[0], f.m0)
+    fast = f.m0 == M32 and f.p[0] == 1 and f.p[1] == M32
+    if fast:
+        e0 = E[0]
+        mi = b.op3("sub.cc.u32", 0, e0)           # -E[0]; borrow <=> E[0] != 0
+        nz = b.op3("subc.u32", 0, 0)              # 0xffffffff if E[0] != 0
+        hi1 = b.op3("add.u32", mi, nz)            # m_i - 1, or 0 when m_i = 0
+    else:
+        mi = b.op3("mul.lo.u32", E[0], f.m0)
     # odd limbs of the modulus -> O pairs
     for j in range(1, n, 2):
+        if fast and j == 1:
+            O[0] = b.op3("add.cc.u32", O[0], e0)
+            O[1] = b.op3("addc.cc.u32", O[1], hi1)
+            continue
         lo = "mad.lo.cc.u32" if j == 1 else "madc.lo.cc.u32"
         O[j - 1] = b.op4(lo, mi, f.p[j], O[j - 1])
         hi = "madc.hi.cc.u32" if j < n - 1 else "madc.hi.u32"
         O[j] = b.op4(hi, mi, f.p[j], O[j])
     # even limbs of the modulus -> E pairs
     for j in range(0, n, 2):
+        if fast and j == 0:
+            E[0] = b.op3("add.cc.u32", E[0], mi)
+            E[1] = b.op3("addc.cc.u32", E[1], 0)
+            continue
         lo = "mad.lo.cc.u32" if j == 0 else "madc.lo.cc.u32"
         E[j] = b.op4(lo, mi, f.p[j], E[j])
         E[j + 1] = b.op4("madc.hi.cc.u32", mi, f.p[j], E[j + 1])

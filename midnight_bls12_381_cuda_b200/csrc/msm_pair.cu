@@ -49,17 +49,20 @@ static void launch_level(const uint32_t* in_off, const uint32_t* out_off, uint32
   constexpr int PB = pair_batch<F>::B, PM = pair_batch<F>::M;
   const uint32_t nt = g * PR_TPB;
   const unsigned gi = (unsigned)((((size_t)nt + 3) / 4 + 127) / 128);   // enough for the smallest per-thread batch (4)
-  static const int minb = [] { const char* e = getenv("B381_BWD_MINB"); return e ? atoi(e) : 4; }();
+  // CTAs per SM of the backward kernel: G1 (126 registers at 4, no spill) measured best at 4 on B200
+  // (profiles/r01b_msm_levels_sweep.txt); G2's Fq2 state needs the full register file: 254 registers, no spill at 2
+  static const int minb = [] { const char* e = getenv("B381_BWD_MINB"); return e ? atoi(e) : 0; }();
+  const int mb = minb ? minb : (sizeof(F) > sizeof(fq_t) ? 2 : 4);
   k_msm_pair_fwd<F, PB, L0><<<g, PR_TPB, 0, st>>>(in_off, out_off, nbuckets, svals, pts, nt, srcg, preg, tot);
   k_msm_invert_totals<F, PB, PM><<<gi, 128, 0, st>>>(out_off, nbuckets, tot);
-  if (minb == 5) k_msm_pair_bwd<F, PB, L0, 5><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
-  else if (minb == 6) k_msm_pair_bwd<F, PB, L0, 6><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
+  if (mb == 2) k_msm_pair_bwd<F, PB, L0, 2><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
+  else if (mb == 3) k_msm_pair_bwd<F, PB, L0, 3><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
   else k_msm_pair_bwd<F, PB, L0, 4><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
 }
 
 // A level pays once there are enough pairs to fill the GPU (each level has ~0.25 ms of fixed latency: three
 // launches and one thread-serial inversion) and buckets are still long.  Measured on B200: 2^20 points -> 2
-// levels, 2^22 -> 4, 2^24 -> 6 (gpurun sweep, profiles/r01_msm_levels_sweep.txt).
+// levels, 2^22 -> 4, 2^24 -> 6 (gpurun sweep, profiles/r01b_msm_levels_sweep.txt).
 int msm_pair_levels(double avg, size_t total) {
   int levels = 0;
   while (levels < 8 && avg >= 8.0 && total / 2 >= ((size_t)1 << 22)) { levels++; avg *= 0.5; total /= 2; }

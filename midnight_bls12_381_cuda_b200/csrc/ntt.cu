@@ -4,6 +4,7 @@
 // Replaces: init_domain_cuda_impl / release_domain_cuda_impl / ntt_cuda_impl / coset_ntt_cuda_impl
 // (bls12-381/src/field/ntt_kernels.cu:1607-1679, :1823-1848, :968-1133, :1155-1306) and the
 // wrappers in bls12-381/src/backend/icicle_field_api.cu:97-131.
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -18,7 +19,10 @@ constexpr uint32_t kNttThreads = 256;
 constexpr uint32_t kMaxDomainLog = 28;            // 2^28 - 1 twiddles = 8 GiB; larger roots are refused
 
 // ------------------------------------------------------------------ kernels
-__global__ void __launch_bounds__(kNttThreads, 3) k_ntt_pass(ntt_pass_params p, const fr_t* in, fr_t* out) {
+// RMAX = stages per register-blocked step: 1 = one butterfly stage per trip through shared memory,
+// 2 = radix-4 steps (4 elements in registers), 3 = radix-8 steps (8 elements, 128 registers, 2 CTAs/SM).
+template <int RMAX>
+__global__ void __launch_bounds__(kNttThreads, RMAX == 3 ? 2 : 3) k_ntt_pass(ntt_pass_params p, const fr_t* in, fr_t* out) {
   extern __shared__ uint4 smem[];
   ntt_tile t;
   const uint32_t tile_elems = 1u << (p.S + p.g + p.x);
@@ -27,11 +31,37 @@ __global__ void __launch_bounds__(kNttThreads, 3) k_ntt_pass(ntt_pass_params p, 
   const uint64_t tile_id = blockIdx.x;
   for (uint32_t pos = threadIdx.x; pos < tile_elems; pos += blockDim.x) ntt_tile_load(p, tile_id, pos, in, t);
   __syncthreads();
-  for (int s = (int)p.S - 1; s >= 0; s--) {
-    for (uint32_t q = threadIdx.x; q < tile_elems / 2; q += blockDim.x) ntt_tile_stage(p, tile_id, q, (uint32_t)s, t);
+  uint32_t s = p.S;
+  while (s > 0) {
+    const uint32_t R = s >= (uint32_t)RMAX ? (uint32_t)RMAX : s;
+    s -= R;
+    const uint32_t groups = tile_elems >> R;
+    for (uint32_t q = threadIdx.x; q < groups; q += blockDim.x) {
+      if (RMAX >= 3 && R == 3) ntt_tile_stages<3>(p, tile_id, q, s, t);
+      else if (RMAX >= 2 && R == 2) ntt_tile_stages<2>(p, tile_id, q, s, t);
+      else ntt_tile_stages<1>(p, tile_id, q, s, t);
+    }
     __syncthreads();
   }
   for (uint32_t pos = threadIdx.x; pos < tile_elems; pos += blockDim.x) ntt_tile_store(p, tile_id, pos, out, t);
+}
+
+static int ntt_rmax() {
+  static const int r = [] { const char* e = getenv("B381_NTT_R"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v > 3 ? 3 : v; }();
+  return r;
+}
+static void launch_ntt_pass(const ntt_pass_params& p, const fr_t* in, fr_t* out, unsigned tiles, size_t smem, cudaStream_t st) {
+  const int r = ntt_rmax();
+  if (r == 3) {
+    cudaFuncSetAttribute(k_ntt_pass<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(uint4) * kTile);
+    k_ntt_pass<3><<<tiles, kNttThreads, smem, st>>>(p, in, out);
+  } else if (r == 2) {
+    cudaFuncSetAttribute(k_ntt_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(uint4) * kTile);
+    k_ntt_pass<2><<<tiles, kNttThreads, smem, st>>>(p, in, out);
+  } else {
+    cudaFuncSetAttribute(k_ntt_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(uint4) * kTile);
+    k_ntt_pass<1><<<tiles, kNttThreads, smem, st>>>(p, in, out);
+  }
 }
 
 // out[j] = base * g^j, j < count, 64 consecutive powers per thread
@@ -242,12 +272,7 @@ static int ntt_run(const fr_t* input, int size, int dir, const b381_ntt_config* 
       const uint32_t tile_log = p.S + p.g + p.x;
       const uint64_t tiles = (total + (1ull << tile_log) - 1) >> tile_log;
       const size_t smem = (size_t)2 * sizeof(uint4) << tile_log;
-      static bool attr_set = false;
-      if (!attr_set) {
-        cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(uint4) * kTile);
-        attr_set = true;
-      }
-      k_ntt_pass<<<(unsigned)tiles, kNttThreads, smem, st>>>(p, src, dst);
+      launch_ntt_pass(p, src, dst, (unsigned)tiles, smem, st);
     }
     lk.unlock();   // tables stay valid: release_domain synchronises the device before freeing
     if ((e = cudaGetLastError()) != cudaSuccess) return map_cuda_error(e);
@@ -293,8 +318,7 @@ static int ntt_dist_columns(fr_t* data, uint32_t log_n, uint32_t log_gpus, uint3
     p.dist_shift = log_gpus; p.dist_logL = logL; p.dist_lo = lo; p.dist_lbase = rank << logL;
     const uint32_t tile_log = p.S + p.g;
     const uint64_t tiles = p.total >> tile_log;
-    cudaFuncSetAttribute(k_ntt_pass, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(uint4) * kTile);
-    k_ntt_pass<<<(unsigned)tiles, kNttThreads, (size_t)2 * sizeof(uint4) << tile_log, st>>>(p, data, data);
+    launch_ntt_pass(p, data, data, (unsigned)tiles, (size_t)2 * sizeof(uint4) << tile_log, st);
     hi -= S;
     rest -= S;
   }

@@ -67,13 +67,18 @@ B381_HD uint32_t bitrev32(uint32_t v, uint32_t bits) {
 }
 
 // shared-memory tile: element e lives as two 16-byte halves in separate arrays so that a warp
-// touching consecutive elements hits all 32 banks exactly once per 8 lanes.
+// touching consecutive elements hits all 32 banks exactly once per 8 lanes.  Slot `pos` is stored at
+// pos ^ ((pos >> 3) & 7): a quarter-warp whose lanes step by 8 slots (the radix-8 step over the three
+// lowest slot bits, one register group per lane) then still spreads over all eight 16-byte bank groups,
+// and lanes on consecutive slots keep doing so (the XOR term is the same for all eight).
 struct ntt_tile {
   uint4* lo;
   uint4* hi;
 };
+B381_HD uint32_t ntt_tile_slot(uint32_t pos) { return pos ^ ((pos >> 3) & 7u); }
 
 B381_DI fr_t tile_get(const ntt_tile& t, uint32_t pos) {
+  pos = ntt_tile_slot(pos);
   uint4 a = t.lo[pos], b = t.hi[pos];
   fr_t r;
   r.l[0] = ((uint64_t)a.y << 32) | a.x; r.l[1] = ((uint64_t)a.w << 32) | a.z;
@@ -84,6 +89,7 @@ B381_DI void tile_put(const ntt_tile& t, uint32_t pos, const fr_t& v) {
   uint4 a, b;
   a.x = (uint32_t)v.l[0]; a.y = (uint32_t)(v.l[0] >> 32); a.z = (uint32_t)v.l[1]; a.w = (uint32_t)(v.l[1] >> 32);
   b.x = (uint32_t)v.l[2]; b.y = (uint32_t)(v.l[2] >> 32); b.z = (uint32_t)v.l[3]; b.w = (uint32_t)(v.l[3] >> 32);
+  pos = ntt_tile_slot(pos);
   t.lo[pos] = a;
   t.hi[pos] = b;
 }
@@ -175,6 +181,48 @@ B381_DI void ntt_tile_stage(const ntt_pass_params& p, uint64_t tile_id, uint32_t
   }
   tile_put(t, pos0, sum);
   tile_put(t, pos1, (k == 0) ? d : mul(d, w));        // stage 0 twiddle is 1
+}
+
+// One butterfly on registers, global stage k = lo + s (+ dist_shift), first element at tile slot pos0.
+B381_DI void ntt_bfly(const ntt_pass_params& p, uint64_t tile_id, uint32_t pos0, uint32_t s, fr_t& a, fr_t& b) {
+  const uint32_t k = p.lo + s + p.dist_shift;
+  const uint64_t I0 = ntt_tile_index(p, tile_id, pos0);
+  const uint32_t j = (uint32_t)(ntt_global_index(p, I0) & ((1ull << k) - 1));
+  const fr_t sum = add(a, b);
+  fr_t d, w;
+  const fr_t* T = p.twiddles + ((1ull << k) - 1);
+  if (!p.inverse || j == 0) {
+    d = sub(a, b);
+    w = fr_gload_ro(T + j);
+  } else {
+    d = sub(b, a);
+    w = fr_gload_ro(T + ((1u << k) - j));
+  }
+  a = sum;
+  b = (k == 0) ? d : mul(d, w);
+}
+
+// phase 2, register-blocked: R consecutive in-pass stages s0+R-1 .. s0 on the 2^R tile slots that differ
+// in slot bits [s0+g, s0+g+R) -- 2^R elements travel smem -> registers -> smem once for R stages
+// (R * 2^(R-1) butterflies), instead of once per stage.  Group q of the tile's 2^(S+g+x-R) groups.
+template <int R>
+B381_DI void ntt_tile_stages(const ntt_pass_params& p, uint64_t tile_id, uint32_t q, uint32_t s0, const ntt_tile& t) {
+  const uint32_t bit0 = s0 + p.g;
+  const uint32_t base = ((q >> bit0) << (bit0 + R)) | (q & ((1u << bit0) - 1));
+  if (ntt_tile_index(p, tile_id, base) >= p.total) return;   // a group never straddles two transforms
+  fr_t v[1 << R];
+#pragma unroll
+  for (int a = 0; a < (1 << R); a++) v[a] = tile_get(t, base | ((uint32_t)a << bit0));
+#pragma unroll
+  for (int r = R - 1; r >= 0; r--) {
+#pragma unroll
+    for (int a = 0; a < (1 << R); a++) {
+      if (a & (1 << r)) continue;
+      ntt_bfly(p, tile_id, base | ((uint32_t)a << bit0), s0 + (uint32_t)r, v[a], v[a | (1 << r)]);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < (1 << R); a++) tile_put(t, base | ((uint32_t)a << bit0), v[a]);
 }
 
 // phase 3: slot `pos` -> global

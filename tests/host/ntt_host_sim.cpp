@@ -18,8 +18,21 @@ static void run_pass(const ntt_pass_params& p, const fr_t* in, fr_t* out) {
   ntt_tile t{lo.data(), hi.data()};
   for (uint64_t tile = 0; tile < tiles; tile++) {
     for (uint32_t pos = 0; pos < te; pos++) ntt_tile_load(p, tile, pos, in, t);
-    for (int s = (int)p.S - 1; s >= 0; s--)
-      for (uint32_t q = 0; q < te / 2; q++) ntt_tile_stage(p, tile, q, (uint32_t)s, t);
+    if (tile & 1) {                        // odd tiles: stage by stage (the plain radix-2 body)
+      for (int s = (int)p.S - 1; s >= 0; s--)
+        for (uint32_t q = 0; q < te / 2; q++) ntt_tile_stage(p, tile, q, (uint32_t)s, t);
+    } else {                               // even tiles: register-blocked steps exactly as k_ntt_pass runs them
+      uint32_t s = p.S;
+      while (s > 0) {
+        const uint32_t R = s >= 3 ? 3u : s;
+        s -= R;
+        for (uint32_t q = 0; q < (te >> R); q++) {
+          if (R == 3) ntt_tile_stages<3>(p, tile, q, s, t);
+          else if (R == 2) ntt_tile_stages<2>(p, tile, q, s, t);
+          else ntt_tile_stages<1>(p, tile, q, s, t);
+        }
+      }
+    }
     for (uint32_t pos = 0; pos < te; pos++) ntt_tile_store(p, tile, pos, out, t);
   }
 }

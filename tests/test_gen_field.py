@@ -29,6 +29,23 @@ def test_ptx_routines_match_bigint(f):
         assert G.run_block(blk["dbl"], f, a) == 2 * a % f.m
 
 
+@pytest.mark.parametrize("f", [G.FQ, G.FR], ids=["fq", "fr"])
+def test_mul_with_degenerate_limbs(f):
+    """operands whose 32-bit limbs are 0 or 0xffffffff: every reduction row of Fr's specialised Montgomery step
+    (m_i = -E[0], the products by the modulus limbs 1 and 0xffffffff replaced by adds) sees E[0] = 0 and
+    E[0] = 0xffffffff, and the carries out of the replaced pairs are exercised."""
+    rnd = random.Random(99)
+    rinv = pow(f.R, -1, f.m)
+    mul = G.build(f, "mul")
+    vals = [1 << 32, 1 << 64, (1 << 96) - (1 << 32), f.m - (1 << 32), 0xFFFFFFFF, 0xFFFFFFFF << 32, (1 << (32 * f.n - 2)) - 1]
+    for _ in range(150):
+        limbs = [rnd.choice((0, 0, 0xFFFFFFFF, 0xFFFFFFFF, 1, rnd.getrandbits(32))) for _ in range(f.n)]
+        vals.append(sum(l << (32 * k) for k, l in enumerate(limbs)) % f.m)
+    for i, a in enumerate(vals):
+        for b in (vals[(5 * i + 1) % len(vals)], a, rnd.randrange(f.m)):
+            assert G.run_block(mul, f, a, b) == a * b * rinv % f.m, (hex(a), hex(b))
+
+
 def test_fr_known_answers():
     f = G.FR
     mul = G.build(f, "mul")
