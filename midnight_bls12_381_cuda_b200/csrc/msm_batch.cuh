@@ -119,23 +119,32 @@ B381_DI void pair_walk(uint32_t slot0, uint32_t n_out, const uint32_t* in_off, c
   }
 }
 
+// x-coordinates alone, one per 64-byte (Fq) / 128-byte (Fq2) aligned record: the level-0 forward pass gathers
+// them at random and needs nothing else, so each gather is one aligned line instead of a 96-byte struct that
+// straddles two (k_pack_x in msm_pair.cu builds the array per call: 0.4 ms at 2^24).
+template <class F> struct alignas(sizeof(F) <= 64 ? 64 : 128) xrec_t { F x; };
+
 template <class F, bool L0>
-B381_DI F pair_load_x(uint32_t pos, const uint32_t* svals, const affine_t<F>* pts) {
-  return L0 ? pts[svals[pos] >> 1].x : pts[pos].x;
+B381_DI F pair_load_x(uint32_t pos, const uint32_t* svals, const affine_t<F>* pts, const xrec_t<F>* xs = nullptr) {
+  if (L0) {
+    uint32_t i = svals[pos] >> 1;
+    return xs ? xs[i].x : pts[i].x;
+  }
+  return pts[pos].x;
 }
 
 // Forward: pre[k*pstride] = product of the denominators before k; returns the product of all B.
 template <class F, int B, bool L0>
 B381_DI F pair_phase1(const uint32_t* src, size_t sstride, const uint32_t* svals, const affine_t<F>* pts, F* pre,
-                      size_t pstride) {
+                      size_t pstride, const xrec_t<F>* xs = nullptr) {
   F acc = one<F>();
 #pragma unroll 4
   for (int k = 0; k < B; k++) {
     uint32_t s = src[(size_t)k * sstride];
     pre[(size_t)k * pstride] = acc;
     if (s & PAIR_SINGLE) continue;          // carried-over point or no slot: no denominator
-    F x1 = pair_load_x<F, L0>(s, svals, pts);
-    F x2 = pair_load_x<F, L0>(s + 1, svals, pts);
+    F x1 = pair_load_x<F, L0>(s, svals, pts, xs);
+    F x2 = pair_load_x<F, L0>(s + 1, svals, pts, xs);
     F d = sub(x2, x1);
     if (is_zero(x1) || is_zero(x2) || is_zero(d)) {   // infinity operand, doubling or cancellation: rare
       affine_t<F> p = pair_load<F, L0>(s, svals, pts);

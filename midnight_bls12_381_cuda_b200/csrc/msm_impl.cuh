@@ -83,8 +83,8 @@ static __global__ void k_msm_half_counts(const uint32_t* offsets, uint32_t nbuck
 int msm_pair_levels(double avg, size_t total);
 template <class F>
 void launch_pair_level(bool level0, const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets,
-                       const uint32_t* svals, const affine_t<F>* pts, unsigned grid, uint32_t* srcg, F* preg, F* tot,
-                       affine_t<F>* out, cudaStream_t st);
+                       const uint32_t* svals, const affine_t<F>* pts, size_t npts, unsigned grid, uint32_t* srcg, F* preg,
+                       F* tot, affine_t<F>* out, cudaStream_t st);
 
 // window sums from the buckets, four lanes per segment: msm_tail.cu
 template <class F>
@@ -282,7 +282,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
         B381_CUDA_TRY(sc.alloc(&tot, (size_t)nt));
       }
       launch_pair_level<F>(l == 0, in_off, out_off, sh.nbuckets, l == 0 ? svals : nullptr,
-                           l == 0 ? d_bases : buf[(l - 1) & 1], g, srcg, preg, tot, buf[l & 1], st);
+                           l == 0 ? d_bases : buf[(l - 1) & 1], (size_t)n * factor, g, srcg, preg, tot, buf[l & 1], st);
       acc_pts = buf[l & 1];
       acc_vals = nullptr;
       in_off = out_off;

@@ -13,12 +13,18 @@ template <class F, int B, bool L0>
 __global__ void __launch_bounds__(PR_TPB, 4) k_msm_pair_fwd(const uint32_t* in_off, const uint32_t* out_off,
                                                             uint32_t nbuckets, const uint32_t* svals,
                                                             const affine_t<F>* pts, uint32_t nt, uint32_t* srcg,
-                                                            F* preg, F* tot) {
+                                                            F* preg, F* tot, const xrec_t<F>* xs) {
   const uint32_t n_out = out_off[nbuckets];
   const uint32_t t = blockIdx.x * PR_TPB + threadIdx.x;
   if ((uint64_t)t * B >= n_out) return;
   pair_walk<B>(t * B, n_out, in_off, out_off, nbuckets, srcg + t, nt);
-  tot[t] = pair_phase1<F, B, L0>(srcg + t, nt, svals, pts, preg + t, nt);
+  tot[t] = pair_phase1<F, B, L0>(srcg + t, nt, svals, pts, preg + t, nt, xs);
+}
+
+template <class F>
+__global__ void k_pack_x(const affine_t<F>* pts, size_t n, xrec_t<F>* xs) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) xs[i].x = pts[i].x;
 }
 
 // in-place inversion of the ceil(n_out / B) thread totals, up to M per thread
@@ -44,7 +50,7 @@ __global__ void __launch_bounds__(PR_TPB, MINB) k_msm_pair_bwd(const uint32_t* o
 
 template <class F, bool L0>
 static void launch_level(const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets, const uint32_t* svals,
-                         const affine_t<F>* pts, unsigned g, uint32_t* srcg, F* preg, F* tot, affine_t<F>* out,
+                         const affine_t<F>* pts, size_t npts, unsigned g, uint32_t* srcg, F* preg, F* tot, affine_t<F>* out,
                          cudaStream_t st) {
   constexpr int PB = pair_batch<F>::B, PM = pair_batch<F>::M;
   const uint32_t nt = g * PR_TPB;
@@ -53,7 +59,17 @@ static void launch_level(const uint32_t* in_off, const uint32_t* out_off, uint32
   // (profiles/r01b_msm_levels_sweep.txt); G2's Fq2 state needs the full register file: 254 registers, no spill at 2
   static const int minb = [] { const char* e = getenv("B381_BWD_MINB"); return e ? atoi(e) : 0; }();
   const int mb = minb ? minb : (sizeof(F) > sizeof(fq_t) ? 2 : 4);
-  k_msm_pair_fwd<F, PB, L0><<<g, PR_TPB, 0, st>>>(in_off, out_off, nbuckets, svals, pts, nt, srcg, preg, tot);
+  xrec_t<F>* xs = nullptr;
+  // Optional (B381_XPACK=1): gather the level-0 x-coordinates from a packed, 64-byte-aligned copy.  Measured on
+  // B200 at 2^24: forward pass 11.1 -> 10.3 ms (DRAM still fetches a 128-byte line per gather: 130 B/gather),
+  // but building the copy costs 0.5 ms -- no net gain, so it is off by default.
+  static const int xpack = [] { const char* e = getenv("B381_XPACK"); return e ? atoi(e) : 0; }();
+  if (L0 && xpack && npts >= ((size_t)1 << 20) && cudaMallocAsync(&xs, npts * sizeof(xrec_t<F>), st) == cudaSuccess)
+    k_pack_x<F><<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(pts, npts, xs);
+  else
+    xs = nullptr;
+  k_msm_pair_fwd<F, PB, L0><<<g, PR_TPB, 0, st>>>(in_off, out_off, nbuckets, svals, pts, nt, srcg, preg, tot, xs);
+  if (xs) cudaFreeAsync(xs, st);
   k_msm_invert_totals<F, PB, PM><<<gi, 128, 0, st>>>(out_off, nbuckets, tot);
   if (mb == 2) k_msm_pair_bwd<F, PB, L0, 2><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
   else if (mb == 3) k_msm_pair_bwd<F, PB, L0, 3><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
@@ -71,15 +87,15 @@ int msm_pair_levels(double avg, size_t total) {
 
 template <class F>
 void launch_pair_level(bool level0, const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets,
-                       const uint32_t* svals, const affine_t<F>* pts, unsigned grid, uint32_t* srcg, F* preg, F* tot,
-                       affine_t<F>* out, cudaStream_t st) {
-  if (level0) launch_level<F, true>(in_off, out_off, nbuckets, svals, pts, grid, srcg, preg, tot, out, st);
-  else launch_level<F, false>(in_off, out_off, nbuckets, nullptr, pts, grid, srcg, preg, tot, out, st);
+                       const uint32_t* svals, const affine_t<F>* pts, size_t npts, unsigned grid, uint32_t* srcg, F* preg,
+                       F* tot, affine_t<F>* out, cudaStream_t st) {
+  if (level0) launch_level<F, true>(in_off, out_off, nbuckets, svals, pts, npts, grid, srcg, preg, tot, out, st);
+  else launch_level<F, false>(in_off, out_off, nbuckets, nullptr, pts, npts, grid, srcg, preg, tot, out, st);
 }
 
 template void launch_pair_level<fq_t>(bool, const uint32_t*, const uint32_t*, uint32_t, const uint32_t*, const affine_t<fq_t>*,
-                                      unsigned, uint32_t*, fq_t*, fq_t*, affine_t<fq_t>*, cudaStream_t);
+                                      size_t, unsigned, uint32_t*, fq_t*, fq_t*, affine_t<fq_t>*, cudaStream_t);
 template void launch_pair_level<fq2_t>(bool, const uint32_t*, const uint32_t*, uint32_t, const uint32_t*, const affine_t<fq2_t>*,
-                                       unsigned, uint32_t*, fq2_t*, fq2_t*, affine_t<fq2_t>*, cudaStream_t);
+                                       size_t, unsigned, uint32_t*, fq2_t*, fq2_t*, affine_t<fq2_t>*, cudaStream_t);
 
 }  // namespace b381

@@ -83,6 +83,27 @@ def test_msm_affine_prereduction_levels(sims):
         assert run_msm(sims, "g2", sc, pts2, 4, 3, 4, levels=levels) == P.g2_result_std_bytes(P.g2_mul(dl, P.G2_GEN))
 
 
+def test_msm_bodies_under_address_sanitizer(sims, tmp_path):
+    """compute-sanitizer is not available on the GPU pool, so the per-thread bodies (slot walk, slot-major scratch
+    indexing, batched inversion, task splitting) are run once under ASan + UBSan with exactly-sized host arrays."""
+    exe = str(tmp_path / "msm_host_sim_asan")
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-D_GLIBCXX_ASSERTIONS", f"-I{HOST}",
+                    f"-I{CSRC}", "-o", exe, os.path.join(HOST, "msm_host_sim.cpp")], check=True)
+    asan = dict(sims)
+    asan["msm_host_sim"] = exe
+    rng = P.SplitMix64(2024)
+    for (group, n, c, K, L, levels) in [("g1", 70, 4, 3, 4, 3), ("g1", 90, 3, 50, 2, 6), ("g2", 14, 4, 3, 4, 2)]:
+        ks = [rng.fr() for _ in range(n)]
+        sc = [rng.fr() for _ in range(n)]
+        sc[1], sc[2] = 0, sc[3]
+        mul, gen = (P.g1_mul, P.G1_GEN) if group == "g1" else (P.g2_mul, P.G2_GEN)
+        pts = [mul(k, gen) for k in ks]
+        pts[5] = None
+        dl = sum(s * k for s, k, p in zip(sc, ks, pts) if p is not None) % P.R_MOD
+        exp = P.g1_result_std_bytes(mul(dl, gen)) if group == "g1" else P.g2_result_std_bytes(mul(dl, gen))
+        assert run_msm(asan, group, sc, pts, c, K, L, levels=levels) == exp, (group, n, levels)
+
+
 def test_msm_pipeline_exceptional_cases(sims):
     # identical bases force the doubling branch of the mixed addition (benches/gpu_msm.rs:30-32)
     assert run_msm(sims, "g1", [5] * 40, [P.G1_GEN] * 40, 4, 3, 2) == P.g1_result_std_bytes(P.g1_mul(200, P.G1_GEN))
