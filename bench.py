@@ -248,7 +248,11 @@ def main():
             if phase_sink is not None:
                 buf = (C.c_float * 12)()
                 cnt = lib.b381_msm_last_timings(buf, 12)
-                phase_sink.append([buf[i] for i in range(cnt)])
+                row = [buf[i] for i in range(cnt)]
+                f_ms, b_ms = C.c_float(), C.c_float()
+                if lib.b381_msm_last_level0_ms(C.byref(f_ms), C.byref(b_ms)) == 1:
+                    row += [f_ms.value, b_ms.value]
+                phase_sink.append(row)
         e1.record()
         barrier()
         t1 = time.perf_counter()
@@ -262,6 +266,8 @@ def main():
         step_resident()
     phases = []
     ms_total, t0, t1 = timed(step_resident, args.steps, phases)
+    msm_info = (C.c_int * 4)()
+    lib.b381_msm_last_info(msm_info, 4)          # shape of the G1 MSM just timed (before any other MSM runs)
     clocks = sampler.window(t0, t1) if sampler else None
     for _ in range(min(args.warmup, 2)):
         step_e2e()
@@ -331,7 +337,7 @@ def main():
         g2_ms, _, _ = timed(g2_step, args.steps, g2_phases)
         g2_ms /= args.steps
         g2 = {"metric": "g2_msm_2^20_points_per_s", "value": n2 / (g2_ms * 1e-3), "unit": "points/s", "ms_per_step": g2_ms,
-              "phases_ms": [round(statistics.mean(c), 4) for c in zip(*g2_phases)], "result": res2}
+              "phases_ms": [round(statistics.mean(c), 4) for c in zip(*g2_phases)][:8], "result": res2}
         del bases2
 
     out = None
@@ -346,9 +352,7 @@ def main():
         ms_step = ms_total / args.steps
         ph = [statistics.mean(c) for c in zip(*phases)] if phases else []
         names = ["digits", "sort", "offsets", "prereduce", "tasks+accumulate", "finalize", "bucket_reduce", "combine"]
-        info = (C.c_int * 4)()
-        lib.b381_msm_last_info(info, 4)
-        c_win, W, levels, own_launches = info[0], info[1], info[2], info[3]
+        c_win, W, levels, own_launches = msm_info[0], msm_info[1], msm_info[2], msm_info[3]
         # Dominant stage = bucket accumulation: `levels` affine pre-reduction levels (k_msm_pair_fwd / k_msm_invert_totals /
         # k_msm_pair_bwd, csrc/msm_batch.cuh) + k_msm_accumulate on what is left.  Algorithmic work per (point, window)
         # insertion as SURVEY.md 8d defines it: one XYZZ mixed addition = 10 Fq products x 300 32x32->64 multiply-adds.
@@ -367,6 +371,16 @@ def main():
                     "algorithmic_unit": "3000 MAD per (point, window) insertion (SURVEY.md 8d); executed: 1800 in the affine levels",
                     "traffic": None, "peak_source": "b381_bench_imad_peak, this run", "kernel_ms": acc_ms,
                     "share_of_step": acc_ms / ms_step, "window_c": c_win, "windows": W, "affine_levels": levels}
+            if len(ph) >= 10 and levels:
+                # the single dominant kernel: level-0 backward pass, 5 Fq products (1500 MADs) per pair sum, n*W/2 pairs
+                pairs = ins / 2.0
+                roof["dominant_kernel"] = {
+                    "name": "k_msm_pair_bwd<fq_t, 32, level 0>", "kernel_ms": ph[9], "share_of_step": ph[9] / ms_step,
+                    "achieved": pairs * 1500.0 / (ph[9] * 1e-3) / 1e9, "unit": "GMAD/s", "frac": pairs * 1500.0 / (ph[9] * 1e-3) / imad_peak,
+                    "note": "carry-chain IMAD.WIDE.X issues at ~0.57 of the plain IMAD.WIDE peak used as denominator (profiles/r01_imad_variants.txt)",
+                    "traffic": 73.5e9 * (n_loc / float(1 << 24)),
+                    "traffic_source": "dram__bytes_read+write of this kernel at n = 2^24, ncu --set full (profiles/r01b_pair_kernels_key_metrics.txt), scaled by n",
+                    "level0_fwd_ms": ph[8]}
         if ntt:
             # n/2 * log2(n) butterflies, one Fr Montgomery product (2*8^2+8 = 136 multiply-adds) each
             ln = n_loc.bit_length() - 1
@@ -414,7 +428,7 @@ def main():
             "gpu_launches_note": "own kernels per MSM step as counted by the library (b381_msm_last_info): digits, offsets, "
                                  "4 per affine level, task_count/build_tasks/task_keys, accumulate, finalize, segment, tree levels, "
                                  "combine, + encode (CUB radix sort / scan kernels not counted)",
-            "phases_ms": dict(zip(names, [round(x, 4) for x in ph])),
+            "phases_ms": dict(zip(names, [round(x, 4) for x in ph[:8]])),
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "ntt": ntt,
             "g2": None if g2 is None else {k: v for k, v in g2.items() if k != "result"},
             "probes": {"imad_wide_mad_per_s": imad_peak, "fq_mul_per_s": fq_rate, "fr_mul_per_s": fr_rate},

@@ -234,6 +234,9 @@ int b381_msm_last_timings(float* out, int cap);
 /* shape of the most recent MSM on this thread: [window bits c, windows W, affine pre-reduction levels,
  * own kernel launches]; returns count written. */
 int b381_msm_last_info(int* out, int cap);
+/* duration of the two dominant kernels of the most recent G1 MSM on this thread (level-0 forward and backward pass
+ * of the affine pre-reduction), CUDA events on the launching stream, B381_MSM_TIMING=1; returns 1 if available. */
+int b381_msm_last_level0_ms(float* fwd_ms, float* bwd_ms);
 const char* b381_version(void);
 
 #ifdef __cplusplus

@@ -80,9 +80,10 @@ B381_DI affine_t<F> pair_finish(int kind, const affine_t<F>& p, const affine_t<F
 }
 
 // ceil(size/2) per bucket; the exclusive scan of these is the next level's offsets
-B381_DI void msm_half_counts_body(uint32_t b, const uint32_t* offsets, uint32_t nbuckets, uint32_t* counts) {
+B381_DI void msm_half_counts_body(uint32_t b, const uint32_t* offsets, uint32_t nbuckets, uint32_t Bs, uint32_t* counts) {
   if (b > nbuckets) return;
-  counts[b] = b < nbuckets ? (offsets[b + 1] - offsets[b] + 1) / 2 : 0u;
+  // trash slots (b % Bs == Bs - 1) produce nothing, so they are empty from level 1 on
+  counts[b] = (b < nbuckets && b % Bs != Bs - 1) ? (offsets[b + 1] - offsets[b] + 1) / 2 : 0u;
 }
 
 // slot -> input pair.  src[k*stride] = position of the pair's first point (| PAIR_SINGLE when the bucket's

@@ -4,10 +4,12 @@
 // checked without a GPU.
 //
 // Pipeline (ours; the reference's is bls12-381/src/curve/msm_kernels.cu:603-903):
-//   1 digits      scalar -> W signed c-bit digits -> (key = w*B + |d|-1, val = idx<<1 | sign);
-//                 zero digits get the trash key W*B.       [ref: compute_bucket_indices_kernel :69-143]
-//   2 sort        device radix sort of (key,val) over ceil(log2(W*B+1)) key bits only
-//                                                           [ref sorts all 32 bits, :768-778]
+//   1 digits      scalar -> W signed c-bit digits -> (key = w*(B+1) + |d|-1, val = idx<<1 | sign);
+//                 zero digits go to the window's own trash bucket, key w*(B+1) + B
+//                                                           [ref: compute_bucket_indices_kernel :69-143]
+//   2 sort        keys are written window-major, so the data is already grouped by window: ONE radix sort
+//                 PER WINDOW over the c bits of the in-window key (2 onesweep passes at c = 16), or, for small
+//                 n / folded windows, one sort over ceil(log2(W*(B+1))) bits   [ref sorts all 32 bits, :768-778]
 //   3 offsets     bucket boundaries straight from the sorted keys (no histogram, no atomics)
 //                                                           [ref: histogram + scan, :224-256,:748-758]
 //   3b pre-reduce affine pairwise levels with CTA-wide batched inversion (msm_batch.cuh): each level
@@ -35,7 +37,8 @@ struct msm_shape {
   uint32_t W;        // number of c-bit windows of the scalar
   uint32_t B;        // buckets per window = 2^(c-1)
   uint32_t Wf;       // bucket sets after folding with precomputed bases: ceil(W / precompute_factor)
-  uint32_t nbuckets; // Wf*B  (key Wf*B is the trash key)
+  uint32_t Bs;       // bucket slots per set = B + 1: slot B of every set is its trash bucket (zero digits)
+  uint32_t nbuckets; // Wf*Bs bucket slots, trash slots included
 };
 
 // With precompute_factor f the caller supplies f*n bases, block k holding 2^(k*Wf*c) * P_i, and
@@ -49,7 +52,8 @@ B381_HD msm_shape make_msm_shape(uint32_t n, uint32_t c, uint32_t bits, uint32_t
   sh.B = 1u << (c - 1);
   if (factor < 1) factor = 1;
   sh.Wf = (sh.W + factor - 1) / factor;
-  sh.nbuckets = sh.Wf * sh.B;
+  sh.Bs = sh.B + 1;
+  sh.nbuckets = sh.Wf * sh.Bs;
   return sh;
 }
 
@@ -61,6 +65,10 @@ B381_HD uint32_t ceil_div_u32(uint32_t a, uint32_t b) { return (a + b - 1) / b; 
 constexpr uint32_t kMaxTasksPerBucket = 1024;
 // buckets with more partials than this are left to the warp-per-bucket finalize kernel
 constexpr uint32_t kFinalizeSerialMax = 8;
+// entries of bucket slot b that count: the trash slot of every set (b % Bs == Bs - 1) holds the zero digits
+B381_HD uint32_t msm_bucket_size(const uint32_t* offsets, uint32_t b, uint32_t Bs) {
+  return (b % Bs == Bs - 1) ? 0u : offsets[b + 1] - offsets[b];
+}
 B381_HD uint32_t msm_tasks_of(uint32_t size, uint32_t K) {
   uint32_t nt = ceil_div_u32(size, K);
   return nt > kMaxTasksPerBucket ? kMaxTasksPerBucket : nt;
@@ -70,8 +78,9 @@ B381_HD uint32_t msm_tasks_of(uint32_t size, uint32_t K) {
 // Signed-digit recoding with the same digit set as the reference
 // (msm_kernels.cu:96-130): d in [-(2^(c-1)-1), 2^(c-1)], d > 2^(c-1) => d -= 2^c, carry.
 // keys/vals are window-major ([w*n + i]) so stores coalesce.
+// local_keys: emit the in-window key only (0..B, B = trash) -- the per-window sort path (needs Wf == W).
 B381_DI void msm_digits_body(uint32_t i, const fr_t* scalars, bool scalars_mont, const msm_shape sh,
-                             uint32_t* keys, uint32_t* vals) {
+                             uint32_t* keys, uint32_t* vals, bool local_keys = false) {
   if (i >= sh.n) return;
   fr_t s = scalars[i];
   if (scalars_mont) s = from_mont(s);
@@ -95,7 +104,7 @@ B381_DI void msm_digits_body(uint32_t i, const fr_t* scalars, bool scalars_mont,
       carry = 1;
     }
     uint32_t blk = w / sh.Wf, wf = w - blk * sh.Wf;
-    uint32_t key = d ? (wf * sh.B + d - 1) : sh.nbuckets;
+    uint32_t key = (local_keys ? 0u : wf * sh.Bs) + (d ? d - 1 : sh.B);
     keys[(size_t)w * sh.n + i] = key;
     vals[(size_t)w * sh.n + i] = ((blk * sh.n + i) << 1) | sign;
   }
@@ -103,30 +112,34 @@ B381_DI void msm_digits_body(uint32_t i, const fr_t* scalars, bool scalars_mont,
 }
 
 // ---------------------------------------------------------------- 3 offsets
-// sorted keys -> offsets[0..nbuckets]; offsets[b] = first position with key >= b.
-// offsets[nbuckets] = number of non-trash entries.
+// sorted keys -> offsets[0..nbuckets]; offsets[b] = first position with key >= b; offsets[nbuckets] = total.
+// n_local != 0: the keys are in-window keys, sorted per window slice of n_local entries; the bucket slot of
+// position j is (j / n_local) * Bs + key, which is monotone over the concatenated slices.
 B381_DI void msm_offsets_body(size_t j, const uint32_t* sorted_keys, size_t total, uint32_t nbuckets,
-                              uint32_t* offsets) {
+                              uint32_t* offsets, uint32_t n_local = 0, uint32_t Bs = 0) {
   if (j > total) return;
-  uint32_t prev = (j == 0) ? 0u : sorted_keys[j - 1] + 1u;          // first key not yet started
-  uint32_t cur = (j == total) ? nbuckets + 1u : sorted_keys[j] + 1u; // one past this key
+  uint32_t kp = 0, kc = 0;
+  if (j > 0) kp = sorted_keys[j - 1] + (n_local ? (uint32_t)((j - 1) / n_local) * Bs : 0u);
+  if (j < total) kc = sorted_keys[j] + (n_local ? (uint32_t)(j / n_local) * Bs : 0u);
+  uint32_t prev = (j == 0) ? 0u : kp + 1u;          // first key not yet started
+  uint32_t cur = (j == total) ? nbuckets + 1u : kc + 1u; // one past this key
   if (j == 0) prev = 0;
   // every bucket id in [prev, cur) starts at position j
   for (uint32_t b = prev; b < cur && b <= nbuckets; b++) offsets[b] = (uint32_t)j;
 }
 
 // ---------------------------------------------------------------- 4 tasks
-B381_DI void msm_task_count_body(uint32_t b, const uint32_t* offsets, uint32_t nbuckets, uint32_t K,
+B381_DI void msm_task_count_body(uint32_t b, const uint32_t* offsets, uint32_t nbuckets, uint32_t Bs, uint32_t K,
                                  uint32_t* counts) {
   if (b >= nbuckets) return;
-  uint32_t sz = offsets[b + 1] - offsets[b];
+  uint32_t sz = msm_bucket_size(offsets, b, Bs);
   counts[b] = msm_tasks_of(sz, K);
 }
 
 B381_DI void msm_build_tasks_body(uint32_t b, const uint32_t* offsets, const uint32_t* task_start,
-                                  uint32_t nbuckets, uint32_t K, uint2* tasks) {
+                                  uint32_t nbuckets, uint32_t Bs, uint32_t K, uint2* tasks) {
   if (b >= nbuckets) return;
-  uint32_t beg = offsets[b], sz = offsets[b + 1] - beg;
+  uint32_t beg = offsets[b], sz = msm_bucket_size(offsets, b, Bs);
   uint32_t nt = msm_tasks_of(sz, K);
   uint32_t t0 = task_start[b];
   // equal split: first (sz % nt) tasks get one extra element
@@ -231,7 +244,7 @@ B381_DI void msm_segment_body(uint32_t gid, uint32_t W, uint32_t B, uint32_t L, 
   uint32_t segs = B / L;
   if (gid >= W * segs) return;
   uint32_t w = gid / segs, s = gid % segs;
-  const xyzz_t<F>* bk = buckets + (size_t)w * B + (size_t)s * L;
+  const xyzz_t<F>* bk = buckets + (size_t)w * (B + 1) + (size_t)s * L;     // B + 1 slots per set (trash last)
   xyzz_t<F> run = xyzz_identity<F>();
   xyzz_t<F> tri = xyzz_identity<F>();
   for (int j = (int)L - 1; j >= 0; j--) {

@@ -19,26 +19,29 @@
 namespace b381 {
 
 // ------------------------------------------------------------------ kernels
-static __global__ void k_msm_digits(const fr_t* scalars, bool mont, msm_shape sh, uint32_t* keys, uint32_t* vals) {
+static __global__ void k_msm_digits(const fr_t* scalars, bool mont, msm_shape sh, uint32_t* keys, uint32_t* vals,
+                                    bool local_keys) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_digits_body(i, scalars, mont, sh, keys, vals);
+  msm_digits_body(i, scalars, mont, sh, keys, vals, local_keys);
 }
 
-static __global__ void k_msm_offsets(const uint32_t* sorted_keys, size_t total, uint32_t nbuckets, uint32_t* offsets) {
+static __global__ void k_msm_offsets(const uint32_t* sorted_keys, size_t total, uint32_t nbuckets, uint32_t* offsets,
+                                     uint32_t n_local, uint32_t Bs) {
   size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  msm_offsets_body(j, sorted_keys, total, nbuckets, offsets);
+  msm_offsets_body(j, sorted_keys, total, nbuckets, offsets, n_local, Bs);
 }
 
-static __global__ void k_msm_task_count(const uint32_t* offsets, uint32_t nbuckets, uint32_t K, uint32_t* counts) {
+static __global__ void k_msm_task_count(const uint32_t* offsets, uint32_t nbuckets, uint32_t Bs, uint32_t K,
+                                        uint32_t* counts) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == nbuckets) counts[b] = 0;  // sentinel so the exclusive scan yields the task total
-  msm_task_count_body(b, offsets, nbuckets, K, counts);
+  msm_task_count_body(b, offsets, nbuckets, Bs, K, counts);
 }
 
 static __global__ void k_msm_build_tasks(const uint32_t* offsets, const uint32_t* task_start, uint32_t nbuckets,
-                                  uint32_t K, uint2* tasks) {
+                                         uint32_t Bs, uint32_t K, uint2* tasks) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_build_tasks_body(b, offsets, task_start, nbuckets, K, tasks);
+  msm_build_tasks_body(b, offsets, task_start, nbuckets, Bs, K, tasks);
 }
 
 static __global__ void k_msm_task_keys(uint32_t max_tasks, const uint32_t* ntasks_dev, const uint2* tasks, uint32_t K,
@@ -71,9 +74,9 @@ template <> inline bool launch_lazy<fq_t>(unsigned g, cudaStream_t st, const uin
 }
 
 // ---- affine pre-reduction (msm_batch.cuh): three kernels per level, no barriers ----------------
-static __global__ void k_msm_half_counts(const uint32_t* offsets, uint32_t nbuckets, uint32_t* counts) {
+static __global__ void k_msm_half_counts(const uint32_t* offsets, uint32_t nbuckets, uint32_t Bs, uint32_t* counts) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_half_counts_body(b, offsets, nbuckets, counts);
+  msm_half_counts_body(b, offsets, nbuckets, Bs, counts);
 }
 
 // The three kernels of a level live in msm_pair.cu (their own translation unit: seconds to compile).
@@ -219,19 +222,56 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
     B381_CUDA_TRY(sc.alloc(&vals[i], total));
   }
   tm.mark();
-  k_msm_digits<<<grid_for(n, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, keys[0], vals[0]);
+  // Keys are written window-major, so one sort PER WINDOW over the c bits of the in-window key does the job
+  // in ceil(c/8) onesweep passes (2 at c = 16) instead of ceil(log2(W*(B+1))/8) (3).  The W separate sorts cost
+  // ~0.8 ms of launches, so this pays from 2^23 points up (B200: 2^24 7.04 -> 5.65 ms, 2^22 1.81 -> 1.97 ms), and
+  // only when windows do not share bucket sets (no precomputed-bases folding).
+  bool per_window = sh.Wf == sh.W && n >= (1u << 23);
+  {
+    const char* e = getenv("B381_MSM_WINDOW_SORT");
+    if (e && e[0]) per_window = sh.Wf == sh.W && e[0] == '1';
+  }
+  k_msm_digits<<<grid_for(n, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, keys[0], vals[0], per_window);
   tm.mark();
 
   // -- 2 sort (only the significant key bits)
-  cub::DoubleBuffer<uint32_t> dk(keys[0], keys[1]), dv(vals[0], vals[1]);
-  int key_bits = (int)ceil_log2_u64((uint64_t)sh.nbuckets + 1);
-  size_t tmp_bytes = 0;
-  B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)total, 0, key_bits, st));
-  uint8_t* tmp = nullptr;
-  B381_CUDA_TRY(sc.alloc(&tmp, tmp_bytes));
-  B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)total, 0, key_bits, st));
-  const uint32_t* skeys = dk.Current();
-  const uint32_t* svals = dv.Current();
+  const uint32_t* skeys;
+  const uint32_t* svals;
+  if (per_window) {
+    const int key_bits = (int)sh.c;               // in-window keys 0 .. B = 2^(c-1)
+    size_t tmp_bytes = 0;
+    {
+      cub::DoubleBuffer<uint32_t> dk(keys[0], keys[1]), dv(vals[0], vals[1]);
+      B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n, 0, key_bits, st));
+    }
+    uint8_t* tmp = nullptr;
+    B381_CUDA_TRY(sc.alloc(&tmp, tmp_bytes));
+    int sel = -1;
+    for (uint32_t w = 0; w < sh.W; w++) {
+      const size_t o = (size_t)w * n;
+      cub::DoubleBuffer<uint32_t> dk(keys[0] + o, keys[1] + o), dv(vals[0] + o, vals[1] + o);
+      B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)n, 0, key_bits, st));
+      const int s_w = dk.Current() == keys[1] + o ? 1 : 0;
+      if (sel < 0) sel = s_w;
+      if (s_w != sel) {        // same size and bit count for every window: the selector cannot differ; be safe anyway
+        B381_CUDA_TRY(cudaMemcpyAsync(keys[sel] + o, keys[s_w] + o, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
+        B381_CUDA_TRY(cudaMemcpyAsync(vals[sel] + o, vals[s_w] + o, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
+      }
+    }
+    skeys = keys[sel];
+    svals = vals[sel];
+  } else {
+    cub::DoubleBuffer<uint32_t> dk(keys[0], keys[1]), dv(vals[0], vals[1]);
+    int key_bits = (int)ceil_log2_u64((uint64_t)sh.nbuckets);
+    if (key_bits < 1) key_bits = 1;
+    size_t tmp_bytes = 0;
+    B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)total, 0, key_bits, st));
+    uint8_t* tmp = nullptr;
+    B381_CUDA_TRY(sc.alloc(&tmp, tmp_bytes));
+    B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)total, 0, key_bits, st));
+    skeys = dk.Current();
+    svals = dv.Current();
+  }
   tm.mark();
 
   // -- 3 offsets
@@ -239,14 +279,14 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   B381_CUDA_TRY(sc.alloc(&offsets, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(sc.alloc(&counts, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(sc.alloc(&task_start, (size_t)sh.nbuckets + 1));
-  k_msm_offsets<<<grid_for(total + 1, 256), 256, 0, st>>>(skeys, total, sh.nbuckets, offsets);
+  k_msm_offsets<<<grid_for(total + 1, 256), 256, 0, st>>>(skeys, total, sh.nbuckets, offsets, per_window ? n : 0u, sh.Bs);
   tm.mark();
 
   // -- 3b affine pre-reduction levels (msm_batch.cuh): each halves every bucket
   const affine_t<F>* acc_pts = d_bases;
   const uint32_t* acc_vals = svals;
   int n_levels = 0;
-  double avg = (double)n * sh.W / (double)sh.nbuckets;   // mean bucket load seen by the accumulate kernel
+  double avg = (double)n * sh.W / ((double)sh.Wf * sh.B);   // mean bucket load seen by the accumulate kernel
   {
     // a level pays once there are enough pairs to fill the GPU and buckets are still long
     int levels = 0;
@@ -267,7 +307,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
       uint32_t *half, *out_off;
       B381_CUDA_TRY(sc.alloc(&half, (size_t)sh.nbuckets + 1));
       B381_CUDA_TRY(sc.alloc(&out_off, (size_t)sh.nbuckets + 1));
-      k_msm_half_counts<<<grid_for((size_t)sh.nbuckets + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, half);
+      k_msm_half_counts<<<grid_for((size_t)sh.nbuckets + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, sh.Bs, half);
       size_t sb = 0;
       B381_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, sb, half, out_off, (int)sh.nbuckets + 1, st));
       uint8_t* stmp = nullptr;
@@ -306,7 +346,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
     const char* e = getenv("B381_MSM_K");
     if (e && atoi(e) > 0) K = (uint32_t)atoi(e);
   }
-  k_msm_task_count<<<grid_for((size_t)sh.nbuckets + 1, 256), 256, 0, st>>>(offsets, sh.nbuckets, K, counts);
+  k_msm_task_count<<<grid_for((size_t)sh.nbuckets + 1, 256), 256, 0, st>>>(offsets, sh.nbuckets, sh.Bs, K, counts);
   size_t scan_bytes = 0;
   B381_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, task_start, (int)sh.nbuckets + 1, st));
   uint8_t* scan_tmp = nullptr;
@@ -315,7 +355,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   const size_t max_tasks = (size_t)sh.nbuckets + total / K + 1;
   uint2* tasks;
   B381_CUDA_TRY(sc.alloc(&tasks, max_tasks));
-  k_msm_build_tasks<<<grid_for(sh.nbuckets, 256), 256, 0, st>>>(offsets, task_start, sh.nbuckets, K, tasks);
+  k_msm_build_tasks<<<grid_for(sh.nbuckets, 256), 256, 0, st>>>(offsets, task_start, sh.nbuckets, sh.Bs, K, tasks);
   // visiting order: longest task first (radix sort of K - len over just enough bits), so the 32 tasks of a
   // warp have near-equal lengths and the grid's tail is made of the shortest ones
   const uint32_t* order = nullptr;
@@ -376,7 +416,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   {
     int tree = 0;
     for (uint32_t half = segs / 2; half >= 1; half >>= 1) tree++;
-    // digits, offsets | 4 per level (+ the offsets copy is a memcpy) | task_count, build_tasks, task_keys,
+    // digits, offsets (CUB sorts not counted) | 4 per level (+ the offsets copy is a memcpy) | task_count, build_tasks, task_keys,
     // accumulate, finalize | segment, tree levels, combine
     g_last_info[0] = (int)sh.c; g_last_info[1] = (int)sh.W; g_last_info[2] = n_levels;
     g_last_info[3] = 2 + 4 * n_levels + 6 + 1 + tree + 1;

@@ -48,6 +48,19 @@ __global__ void __launch_bounds__(PR_TPB, MINB) k_msm_pair_bwd(const uint32_t* o
   pair_phase2<F, B, L0>(tot[t], srcg + t, nt, svals, pts, preg + t, nt, out + (size_t)t * B);
 }
 
+// Live timing of the dominant kernels (level-0 forward and backward pass) for bench.py's roofline, recorded on
+// the launching stream when B381_MSM_TIMING=1 and read back through b381_msm_last_level0_ms.
+static thread_local cudaEvent_t g_l0_ev[4];
+static thread_local bool g_l0_ev_init = false, g_l0_ev_valid = false;
+static bool l0_timing_on() {
+  static const bool on = [] { const char* e = getenv("B381_MSM_TIMING"); return e && e[0] == '1'; }();
+  if (on && !g_l0_ev_init) {
+    for (auto& e : g_l0_ev) cudaEventCreate(&e);
+    g_l0_ev_init = true;
+  }
+  return on;
+}
+
 template <class F, bool L0>
 static void launch_level(const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets, const uint32_t* svals,
                          const affine_t<F>* pts, size_t npts, unsigned g, uint32_t* srcg, F* preg, F* tot, affine_t<F>* out,
@@ -68,12 +81,20 @@ static void launch_level(const uint32_t* in_off, const uint32_t* out_off, uint32
     k_pack_x<F><<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(pts, npts, xs);
   else
     xs = nullptr;
+  const bool timed = L0 && sizeof(F) == sizeof(fq_t) && l0_timing_on();
+  if (timed) cudaEventRecord(g_l0_ev[0], st);
   k_msm_pair_fwd<F, PB, L0><<<g, PR_TPB, 0, st>>>(in_off, out_off, nbuckets, svals, pts, nt, srcg, preg, tot, xs);
+  if (timed) cudaEventRecord(g_l0_ev[1], st);
   if (xs) cudaFreeAsync(xs, st);
   k_msm_invert_totals<F, PB, PM><<<gi, 128, 0, st>>>(out_off, nbuckets, tot);
+  if (timed) cudaEventRecord(g_l0_ev[2], st);
   if (mb == 2) k_msm_pair_bwd<F, PB, L0, 2><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
   else if (mb == 3) k_msm_pair_bwd<F, PB, L0, 3><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
   else k_msm_pair_bwd<F, PB, L0, 4><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
+  if (timed) {
+    cudaEventRecord(g_l0_ev[3], st);
+    g_l0_ev_valid = true;
+  }
 }
 
 // A level pays once there are enough pairs to fill the GPU (each level has ~0.25 ms of fixed latency: three
@@ -99,3 +120,12 @@ template void launch_pair_level<fq2_t>(bool, const uint32_t*, const uint32_t*, u
                                        size_t, unsigned, uint32_t*, fq2_t*, fq2_t*, affine_t<fq2_t>*, cudaStream_t);
 
 }  // namespace b381
+
+extern "C" int b381_msm_last_level0_ms(float* fwd_ms, float* bwd_ms) {
+  using namespace b381;
+  if (!g_l0_ev_valid || !fwd_ms || !bwd_ms) return 0;
+  if (cudaEventSynchronize(g_l0_ev[3]) != cudaSuccess) return 0;
+  if (cudaEventElapsedTime(fwd_ms, g_l0_ev[0], g_l0_ev[1]) != cudaSuccess) return 0;
+  if (cudaEventElapsedTime(bwd_ms, g_l0_ev[2], g_l0_ev[3]) != cudaSuccess) return 0;
+  return 1;
+}

@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(128) k_msm_segment_coop(uint32_t W, uint32_t B
   const bool live = gid < W * segs;       // dead groups still run the shuffles (on segment 0)
   const uint32_t g = live ? gid : 0;
   const uint32_t w = g / segs, s = g % segs;
-  const xyzz_t<F>* bk = buckets + (size_t)w * B + (size_t)s * L;
+  const xyzz_t<F>* bk = buckets + (size_t)w * (B + 1) + (size_t)s * L;     // B + 1 slots per set (trash last)
   xyzz_t<F> run = xyzz_identity<F>();
   xyzz_t<F> tri = xyzz_identity<F>();
 #pragma unroll 1

@@ -37,21 +37,29 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint
   }
   size_t total = (size_t)n * sh.W;
   std::vector<uint32_t> keys(total), vals(total);
-  for (uint32_t i = 0; i < n; i++) msm_digits_body(i, sc.data(), mont, sh, keys.data(), vals.data());
+  // n odd + unfolded windows: exercise the per-window sort path (in-window keys, one sort per window slice)
+  const bool per_window = sh.Wf == sh.W && (n & 1);
+  for (uint32_t i = 0; i < n; i++) msm_digits_body(i, sc.data(), mont, sh, keys.data(), vals.data(), per_window);
   std::vector<size_t> perm(total);
   std::iota(perm.begin(), perm.end(), 0);
-  std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+  if (per_window) {
+    for (uint32_t w = 0; w < sh.W; w++)
+      std::stable_sort(perm.begin() + (size_t)w * n, perm.begin() + (size_t)(w + 1) * n,
+                       [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+  } else {
+    std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
+  }
   std::vector<uint32_t> sk(total), sv(total);
   for (size_t j = 0; j < total; j++) { sk[j] = keys[perm[j]]; sv[j] = vals[perm[j]]; }
   std::vector<uint32_t> offsets(sh.nbuckets + 1, 0xdeadbeef);
-  for (size_t j = 0; j <= total; j++) msm_offsets_body(j, sk.data(), total, sh.nbuckets, offsets.data());
+  for (size_t j = 0; j <= total; j++) msm_offsets_body(j, sk.data(), total, sh.nbuckets, offsets.data(), per_window ? n : 0u, sh.Bs);
   // affine pre-reduction levels
   const uint32_t* cur_vals = sv.data();
   std::vector<affine_t<F>> lvl_pts;
   for (uint32_t l = 0; l < levels; l++) {
     constexpr int PB = 3;
     std::vector<uint32_t> half(sh.nbuckets + 1), next_off(sh.nbuckets + 1);
-    for (uint32_t b = 0; b <= sh.nbuckets; b++) msm_half_counts_body(b, offsets.data(), sh.nbuckets, half.data());
+    for (uint32_t b = 0; b <= sh.nbuckets; b++) msm_half_counts_body(b, offsets.data(), sh.nbuckets, sh.Bs, half.data());
     uint32_t run_sum = 0;
     for (uint32_t b = 0; b <= sh.nbuckets; b++) { next_off[b] = run_sum; run_sum += half[b]; }
     uint32_t n_out = next_off[sh.nbuckets];
@@ -80,11 +88,11 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint
   }
   if (levels) { pts = lvl_pts; cur_vals = nullptr; }
   std::vector<uint32_t> counts(sh.nbuckets), tstart(sh.nbuckets);
-  for (uint32_t b = 0; b < sh.nbuckets; b++) msm_task_count_body(b, offsets.data(), sh.nbuckets, K, counts.data());
+  for (uint32_t b = 0; b < sh.nbuckets; b++) msm_task_count_body(b, offsets.data(), sh.nbuckets, sh.Bs, K, counts.data());
   uint32_t ntasks = 0;
   for (uint32_t b = 0; b < sh.nbuckets; b++) { tstart[b] = ntasks; ntasks += counts[b]; }
   std::vector<uint2> tasks(ntasks ? ntasks : 1);
-  for (uint32_t b = 0; b < sh.nbuckets; b++) msm_build_tasks_body(b, offsets.data(), tstart.data(), sh.nbuckets, K, tasks.data());
+  for (uint32_t b = 0; b < sh.nbuckets; b++) msm_build_tasks_body(b, offsets.data(), tstart.data(), sh.nbuckets, sh.Bs, K, tasks.data());
   std::vector<xyzz_t<F>> partial(ntasks ? ntasks : 1), buckets(sh.nbuckets);
   for (uint32_t t = 0; t < ntasks; t++) msm_accumulate_body<F>(t, ntasks, tasks.data(), cur_vals, pts.data(), partial.data());
   for (uint32_t b = 0; b < sh.nbuckets; b++) msm_finalize_body<F>(b, sh.nbuckets, tstart.data(), counts.data(), partial.data(), buckets.data());
