@@ -153,6 +153,18 @@ int b381_vector_mul(const b381_fr* a, const b381_fr* b, uint64_t size, const b38
 int b381_scalar_mul_vec(const b381_fr* scalar_a, const b381_fr* b, uint64_t size, const b381_vecops_config* config, b381_fr* out);
 int b381_scalar_add_vec(const b381_fr* scalar_a, const b381_fr* b, uint64_t size, const b381_vecops_config* config, b381_fr* out);
 
+/* ---- unregistered ops the reference's callers use on the same vectors ---- */
+/* out[0] = sum a[i]  (vec_sum_cuda, vec_ops.cu:479-520) */
+int b381_vector_sum(const b381_fr* a, uint64_t size, const b381_vecops_config* config, b381_fr* out);
+/* out[i] = a[i]^-1, 0 -> 0; Montgomery's trick + one variable-time inversion per 32 elements
+ * (batch_inv_cuda, vec_ops.cu:606-677) */
+int b381_vector_inv(const b381_fr* a, uint64_t size, const b381_vecops_config* config, b381_fr* out);
+/* out[bitrev(i)] = a[i], size a power of two; in place when out == a on the device
+ * (icicle bit_reverse / bit_reverse_inplace as called by core/vecops.rs:392-535) */
+int b381_bit_reverse(const b381_fr* a, uint64_t size, const b381_vecops_config* config, b381_fr* out);
+/* standard <-> Montgomery form (field_to_montgomery / field_from_montgomery, field.cuh:906-928) */
+int b381_montgomery_convert(const b381_fr* a, uint64_t size, int to_montgomery, const b381_vecops_config* config, b381_fr* out);
+
 /* ======================= reference-named flat test API ======================= */
 /* icicle_curve_api.cu:679-706: Montgomery points, INTEGER-form scalars unless the config flag says
  * Montgomery, DEVICE-or-host per flags, result Jacobian in Montgomery form (Z = R or 0). */
@@ -173,6 +185,14 @@ int bls12_381_field_ntt_release_domain_cuda(void);
 int bls12_381_vector_add(const b381_fr* a, const b381_fr* b, uint64_t size, const b381_vecops_config* config, b381_fr* out);
 int bls12_381_vector_sub(const b381_fr* a, const b381_fr* b, uint64_t size, const b381_vecops_config* config, b381_fr* out);
 int bls12_381_vector_mul(const b381_fr* a, const b381_fr* b, uint64_t size, const b381_vecops_config* config, b381_fr* out);
+
+/* vec_ops.cu:393-520: DEVICE vectors, output first; the scalar of scalar_*_vec_cuda is read on the HOST */
+int vec_add_cuda(b381_fr* out, const b381_fr* a, const b381_fr* b, int size, const b381_vecops_config* config);
+int vec_sub_cuda(b381_fr* out, const b381_fr* a, const b381_fr* b, int size, const b381_vecops_config* config);
+int vec_mul_cuda(b381_fr* out, const b381_fr* a, const b381_fr* b, int size, const b381_vecops_config* config);
+int scalar_mul_vec_cuda(b381_fr* out, const b381_fr* scalar, const b381_fr* vec, int size, const b381_vecops_config* config);
+int scalar_add_vec_cuda(b381_fr* out, const b381_fr* scalar, const b381_fr* vec, int size, const b381_vecops_config* config);
+int vec_sum_cuda(b381_fr* out, const b381_fr* a, int size, const b381_vecops_config* config);
 
 /* ======================= device plumbing (CudaDeviceAPI, src/device/cuda_device_api.cu:38-149) ==== */
 int b381_device_count(int* count);

@@ -303,6 +303,27 @@ inline std::vector<Scalar> vector_sub(const std::vector<Scalar>& a, const std::v
 inline std::vector<Scalar> vector_mul(const std::vector<Scalar>& a, const std::vector<Scalar>& b) { detail::same_len(a, b); return detail::binary(b381_vector_mul, a.data(), b, "vector_mul"); }
 inline std::vector<Scalar> scalar_mul(const Scalar& s, const std::vector<Scalar>& a) { return detail::binary(b381_scalar_mul_vec, &s, a, "scalar_mul"); }
 inline std::vector<Scalar> scalar_add(const Scalar& s, const std::vector<Scalar>& a) { return detail::binary(b381_scalar_add_vec, &s, a, "scalar_add"); }
+// core/vecops.rs:392-535
+inline std::vector<Scalar> bit_reverse(const std::vector<Scalar>& a) {
+  if (a.size() & (a.size() - 1)) throw Error(B381_INVALID_ARGUMENT, "bit_reverse requires power of 2 length");
+  std::vector<Scalar> out(a.size());
+  b381_vecops_config c = b381_default_vecops_config();
+  check(b381_bit_reverse(a.data(), a.size(), &c, out.data()), "bit_reverse");
+  return out;
+}
+inline void bit_reverse_inplace(std::vector<Scalar>& a) { a = bit_reverse(a); }
+inline Scalar vector_sum(const std::vector<Scalar>& a) {
+  Scalar out{};
+  b381_vecops_config c = b381_default_vecops_config();
+  check(b381_vector_sum(a.data(), a.size(), &c, &out), "vector_sum");
+  return out;
+}
+inline std::vector<Scalar> batch_inverse(const std::vector<Scalar>& a) {
+  std::vector<Scalar> out(a.size());
+  b381_vecops_config c = b381_default_vecops_config();
+  check(b381_vector_inv(a.data(), a.size(), &c, out.data()), "batch_inverse");
+  return out;
+}
 }  // namespace vecops
 
 }  // namespace b381

@@ -11,7 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def declared_functions():
     src = open(os.path.join(ROOT, "include", "b381.h")).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b((?:b381|bls12_381)_[a-z0-9_]+)\s*\(", src)))
+    # b381_* / bls12_381_* plus the reference's unprefixed flat test names (vec_add_cuda, scalar_mul_vec_cuda, ...)
+    return sorted(set(re.findall(r"\b((?:b381|bls12_381)_[a-z0-9_]+|(?:vec|scalar)_[a-z_]+_cuda)\s*\(", src)))
 
 
 def test_every_declared_symbol_is_exported(b381):
