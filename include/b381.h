@@ -194,6 +194,18 @@ int scalar_mul_vec_cuda(b381_fr* out, const b381_fr* scalar, const b381_fr* vec,
 int scalar_add_vec_cuda(b381_fr* out, const b381_fr* scalar, const b381_fr* vec, int size, const b381_vecops_config* config);
 int vec_sum_cuda(b381_fr* out, const b381_fr* a, int size, const b381_vecops_config* config);
 
+/* ---- point formats and ingest validation (point_ops.cu:759-1000, point.cuh:339-387) ----
+ * Jacobian (X, Y, Z) Montgomery, x = X/Z^2, y = Y/Z^3, infinity (0, R, 0) <-> affine Montgomery, infinity (0, 0).
+ * projective_to_affine shares one inversion between 16 points (the reference inverts every Z separately).
+ * Residency per config->is_a_on_device / is_result_on_device; 0 < size <= 2^26 like the reference. */
+int bls12_381_g1_affine_to_projective(const b381_g1_affine* in, int size, const b381_vecops_config* config, b381_g1_projective* out);
+int bls12_381_g1_projective_to_affine(const b381_g1_projective* in, int size, const b381_vecops_config* config, b381_g1_affine* out);
+int bls12_381_g2_affine_to_projective(const b381_g2_affine* in, int size, const b381_vecops_config* config, b381_g2_projective* out);
+int bls12_381_g2_projective_to_affine(const b381_g2_projective* in, int size, const b381_vecops_config* config, b381_g2_affine* out);
+/* flags[i] = 1 if point i is infinity or satisfies y^2 = x^3 + 4 (G1) / y^2 = x^3 + 4(1+u) (G2), else 0 */
+int b381_g1_is_on_curve(const b381_g1_affine* in, int size, const b381_vecops_config* config, uint8_t* flags);
+int b381_g2_is_on_curve(const b381_g2_affine* in, int size, const b381_vecops_config* config, uint8_t* flags);
+
 /* ======================= device plumbing (CudaDeviceAPI, src/device/cuda_device_api.cu:38-149) ==== */
 int b381_device_count(int* count);
 int b381_set_device(int device_id);

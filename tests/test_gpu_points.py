@@ -1,0 +1,110 @@
+"""Point-format conversions and on-curve validation on the GPU, through the C ABI with
+the reference's entry-point names (bls12-381/src/curve/point_ops.cu:759-1000), against Python big integers."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import pyref as P
+
+pytestmark = pytest.mark.gpu
+
+
+def fq_m(v):
+    return P.fq_bytes(P.fq_to_mont(v % P.P_MOD))
+
+
+def g1_jac_bytes(pt, z):
+    """(x z^2, y z^3, z) Montgomery; infinity = (0, R, 0) (point.cuh:469-486)."""
+    if pt is None:
+        return fq_m(0) + fq_m(1) + fq_m(0)
+    x, y = pt
+    return fq_m(x * z * z) + fq_m(y * z * z * z) + fq_m(z)
+
+
+def fq2_m(v):
+    return fq_m(v.c0) + fq_m(v.c1)
+
+
+def g2_jac_bytes(pt, z):
+    if pt is None:
+        return fq2_m(P.Fq2(0, 0)) + fq2_m(P.Fq2(1, 0)) + fq2_m(P.Fq2(0, 0))
+    x, y = pt
+    return fq2_m(x * z * z) + fq2_m(y * z * z * z) + fq2_m(z)
+
+
+def call(b381, name, inp, n, out, on_device=False):
+    lib = b381.lib()
+    cfg = lib.b381_default_vecops_config()
+    cfg.is_a_on_device = cfg.is_result_on_device = on_device
+    return getattr(lib, name)(b381.ptr(inp), n, C.byref(cfg), b381.ptr(out))
+
+
+@pytest.mark.parametrize("n", [1, 5, 33, 1000])
+def test_g1_conversions(cuda, b381, n):
+    rng = P.SplitMix64(900 + n)
+    pts = [P.g1_mul(rng.fr(), P.G1_GEN) for _ in range(min(n, 40))]
+    pts = (pts * (n // len(pts) + 1))[:n]
+    zs = [rng.fr() % P.P_MOD or 1 for _ in range(n)]
+    if n > 3:
+        pts[2] = None
+        zs[0] = 1
+    jac = np.frombuffer(b"".join(g1_jac_bytes(p, z) for p, z in zip(pts, zs)), dtype=np.uint64).copy()
+    aff_exp = b"".join(P.g1_affine_mont_bytes(p) for p in pts)
+    out = np.zeros(12 * n, dtype=np.uint64)
+    assert call(b381, "bls12_381_g1_projective_to_affine", jac, n, out) == 0
+    assert out.tobytes() == aff_exp
+    # device-resident in/out
+    d_in, d_out = cuda.from_numpy(jac.view(np.int64)).cuda(), cuda.zeros(12 * n, dtype=cuda.int64, device="cuda")
+    assert call(b381, "bls12_381_g1_projective_to_affine", d_in, n, d_out, on_device=True) == 0
+    assert d_out.cpu().numpy().tobytes() == aff_exp
+    # affine -> Jacobian is (x, y, R) / (0, R, 0), and converting back is the identity
+    aff = np.frombuffer(aff_exp, dtype=np.uint64).copy()
+    j2 = np.zeros(18 * n, dtype=np.uint64)
+    assert call(b381, "bls12_381_g1_affine_to_projective", aff, n, j2) == 0
+    assert j2.tobytes() == b"".join(g1_jac_bytes(p, 1) for p in pts)
+    back = np.zeros(12 * n, dtype=np.uint64)
+    assert call(b381, "bls12_381_g1_projective_to_affine", j2, n, back) == 0
+    assert back.tobytes() == aff_exp
+
+
+def test_g2_conversions(cuda, b381):
+    rng = P.SplitMix64(77)
+    n = 37
+    pts = [P.g2_mul(rng.fr(), P.G2_GEN) for _ in range(8)]
+    pts = (pts * 5)[:n]
+    pts[4] = None
+    zs = [P.Fq2(rng.fr(), rng.fr()) for _ in range(n)]
+    jac = np.frombuffer(b"".join(g2_jac_bytes(p, z) for p, z in zip(pts, zs)), dtype=np.uint64).copy()
+    aff_exp = b"".join(P.g2_affine_mont_bytes(p) for p in pts)
+    out = np.zeros(24 * n, dtype=np.uint64)
+    assert call(b381, "bls12_381_g2_projective_to_affine", jac, n, out) == 0
+    assert out.tobytes() == aff_exp
+    j2 = np.zeros(36 * n, dtype=np.uint64)
+    assert call(b381, "bls12_381_g2_affine_to_projective", np.frombuffer(aff_exp, dtype=np.uint64).copy(), n, j2) == 0
+    assert j2.tobytes() == b"".join(g2_jac_bytes(p, P.Fq2(1, 0)) for p in pts)
+
+
+def test_on_curve_and_argument_errors(cuda, b381):
+    rng = P.SplitMix64(5)
+    n = 64
+    pts = [P.g1_mul(rng.fr(), P.G1_GEN) for _ in range(n)]
+    pts[3] = None
+    raw = bytearray(b"".join(P.g1_affine_mont_bytes(p) for p in pts))
+    bad = {7, 20, 63}
+    for i in bad:                      # corrupt y: off the curve
+        raw[96 * i + 48] ^= 1
+    flags = np.zeros(n, dtype=np.uint8)
+    assert call(b381, "b381_g1_is_on_curve", np.frombuffer(bytes(raw), dtype=np.uint64).copy(), n, flags) == 0
+    assert [i for i in range(n) if not flags[i]] == sorted(bad)
+    pts2 = [P.g2_mul(rng.fr(), P.G2_GEN) for _ in range(9)] + [None]
+    raw2 = bytearray(b"".join(P.g2_affine_mont_bytes(p) for p in pts2))
+    raw2[192 * 2 + 5] ^= 4
+    f2 = np.zeros(10, dtype=np.uint8)
+    assert call(b381, "b381_g2_is_on_curve", np.frombuffer(bytes(raw2), dtype=np.uint64).copy(), 10, f2) == 0
+    assert list(f2) == [1, 1, 0, 1, 1, 1, 1, 1, 1, 1]
+    # the reference's argument checks (point_ops.cu:766-775): null pointers and size <= 0 -> INVALID_ARGUMENT
+    lib = b381.lib()
+    cfg = lib.b381_default_vecops_config()
+    assert lib.bls12_381_g1_projective_to_affine(None, 4, C.byref(cfg), b381.ptr(flags)) == 11
+    assert lib.bls12_381_g1_projective_to_affine(b381.ptr(flags), 0, C.byref(cfg), b381.ptr(flags)) == 11
