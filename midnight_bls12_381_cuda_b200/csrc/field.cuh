@@ -15,6 +15,7 @@
 #define B381_HD inline
 #else
 #include "field_ptx.cuh"
+#include "raw_ptx.cuh"
 #define B381_DI __device__ __forceinline__
 #define B381_HD __host__ __device__ __forceinline__
 #endif
@@ -94,12 +95,18 @@ B381_DI fr_t inv(const fr_t& a) { const uint64_t m[4] = FR_MODULUS_INIT; return 
 // every round (ncu: 211 k instructions per warp-inversion).  Invariants, sigma = +-1 flipping on a swap:
 //   u*s + v*r = p,   a*r = -sigma*u*2^k,   a*s = sigma*v*2^k  (mod p).
 B381_HD uint64_t raw6_add(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+#if defined(__CUDA_ARCH__)
+  return raw6_add_ptx(r, a, b);
+#endif
   unsigned __int128 c = 0;
 #pragma unroll
   for (int i = 0; i < 6; i++) { c += (unsigned __int128)a[i] + b[i]; r[i] = (uint64_t)c; c >>= 64; }
   return (uint64_t)c;
 }
 B381_HD uint64_t raw6_sub(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+#if defined(__CUDA_ARCH__)
+  return raw6_sub_ptx(r, a, b);
+#endif
   uint64_t br = 0;
 #pragma unroll
   for (int i = 0; i < 6; i++) {
@@ -108,6 +115,17 @@ B381_HD uint64_t raw6_sub(uint64_t* r, const uint64_t* a, const uint64_t* b) {
     br = (uint64_t)(d >> 64) & 1;
   }
   return br;
+}
+// m ? a : b for an all-ones / all-zeros mask: two LOP3 on the device (the plain expression becomes SEL + LOP3 pairs)
+B381_HD uint64_t sel64(uint64_t m, uint64_t a, uint64_t b) {
+#if defined(__CUDA_ARCH__)
+  uint32_t rl, rh;
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(rl) : "r"((uint32_t)a), "r"((uint32_t)b), "r"((uint32_t)m));
+  asm("lop3.b32 %0, %1, %2, %3, 0xE4;" : "=r"(rh) : "r"((uint32_t)(a >> 32)), "r"((uint32_t)(b >> 32)), "r"((uint32_t)(m >> 32)));
+  return ((uint64_t)rh << 32) | rl;
+#else
+  return (a & m) | (b & ~m);
+#endif
 }
 B381_HD void raw6_shr1(uint64_t* a) {
 #pragma unroll
@@ -137,11 +155,11 @@ B381_DI fq_t inv_vartime(const fq_t& a) {
     const uint64_t swp = odd & (0 - lt);
 #pragma unroll
     for (int i = 0; i < 6; i++) {
-      uint64_t vn = (t1[i] & ~swp) | (t2[i] & swp);
-      uint64_t vi = (v[i] & ~odd) | (vn & odd);
-      u[i] = (u[i] & ~swp) | (v[i] & swp);
-      uint64_t rn = (r[i] & ~swp) | (s[i] & swp);
-      s[i] = (s[i] & ~odd) | (ss[i] & odd);
+      uint64_t vn = sel64(swp, t2[i], t1[i]);
+      uint64_t vi = sel64(odd, vn, v[i]);
+      u[i] = sel64(swp, v[i], u[i]);
+      uint64_t rn = sel64(swp, s[i], r[i]);
+      s[i] = sel64(odd, ss[i], s[i]);
       r[i] = rn;
       v[i] = vi;
     }

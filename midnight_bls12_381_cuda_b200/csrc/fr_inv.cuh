@@ -10,6 +10,9 @@ namespace b381 {
 
 template <int N>
 B381_HD uint64_t rawn_add(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+#if defined(__CUDA_ARCH__)
+  if (N == 4) return raw4_add_ptx(r, a, b);
+#endif
   unsigned __int128 c = 0;
 #pragma unroll
   for (int i = 0; i < N; i++) { c += (unsigned __int128)a[i] + b[i]; r[i] = (uint64_t)c; c >>= 64; }
@@ -17,6 +20,9 @@ B381_HD uint64_t rawn_add(uint64_t* r, const uint64_t* a, const uint64_t* b) {
 }
 template <int N>
 B381_HD uint64_t rawn_sub(uint64_t* r, const uint64_t* a, const uint64_t* b) {
+#if defined(__CUDA_ARCH__)
+  if (N == 4) return raw4_sub_ptx(r, a, b);
+#endif
   uint64_t br = 0;
 #pragma unroll
   for (int i = 0; i < N; i++) {
@@ -46,11 +52,11 @@ B381_DI fr_t inv_vartime(const fr_t& a) {
     const uint64_t swp = odd & (0 - lt);
 #pragma unroll
     for (int i = 0; i < N; i++) {
-      uint64_t vn = (t1[i] & ~swp) | (t2[i] & swp);
-      uint64_t vi = (v[i] & ~odd) | (vn & odd);
-      u[i] = (u[i] & ~swp) | (v[i] & swp);
-      uint64_t rn = (r[i] & ~swp) | (s[i] & swp);
-      s[i] = (s[i] & ~odd) | (ss[i] & odd);
+      uint64_t vn = sel64(swp, t2[i], t1[i]);
+      uint64_t vi = sel64(odd, vn, v[i]);
+      u[i] = sel64(swp, v[i], u[i]);
+      uint64_t rn = sel64(swp, s[i], r[i]);
+      s[i] = sel64(odd, ss[i], s[i]);
       r[i] = rn;
       v[i] = vi;
     }
