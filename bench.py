@@ -165,8 +165,7 @@ def main():
     M.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"      # keep stdout to the ONE JSON line (NCCL prints its version there)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's version / debug lines go to stderr: stdout is the ONE JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     lib = L.lib()
     os.environ["B381_MSM_TIMING"] = "1"
