@@ -54,6 +54,7 @@ def parse():
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--cpu-log-n", type=int, default=0, help="log2 size of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--dist-ntt-log", type=int, default=26, help="log2 size of the four-step NTT timed at N > 1")
     return ap.parse_args()
 
 
@@ -143,6 +144,138 @@ def run_reference(args):
 
 
 # ----------------------------------------------------------------------------- GPU arm
+def canonical_fr(torch, count, seed):
+    """`count` canonical Fr values as [count, 4] int64 device words (top limb below r's top limb)."""
+    gen = torch.Generator(device="cuda").manual_seed(seed)
+    v = torch.randint(0, 1 << 62, (count, 4), dtype=torch.int64, device="cuda", generator=gen)
+    v[:, 3] = torch.randint(0, R_TOP_LIMB, (count,), dtype=torch.int64, device="cuda", generator=gen)
+    return v
+
+
+def multi_gpu_legs(args, torch, dist, np, M, L, D, lib, rank, world, local_rank, n, sc, result, timed, barrier):
+    """What only exists at N > 1, on real NCCL (BASELINE.json configs 3 and 5):
+    (1) sharded-MSM parity: the all_gather'ed result of the timed step against ONE single-GPU MSM over all points,
+        run on rank 0 from the gathered scalars;
+    (2) Fr NTT 2^26 four-step over the N GPUs (column stages, ONE all_to_all of row blocks over NVLink, row
+        transforms): every rank compares its row block with its own single-GPU kNR transform of the same vector,
+        both directions, then the forward transform is timed (max over ranks) with the three phases split by events;
+    (3) the commitment MSMs of a k = 22 PLONK prover round: 8 scalar vectors over shared resident bases, dealt
+        round-robin to the ranks (no data-path collective; 144-byte results all_gather'ed), checked against rank 0
+        computing all eight alone."""
+    g = np.array(G1_GEN_MONT, dtype=np.uint64)
+    dev_cfg = lib.b381_default_msm_config()
+    dev_cfg.are_scalars_on_device = dev_cfg.are_points_on_device = True
+    dev_cfg.are_scalars_montgomery_form = dev_cfg.are_points_montgomery_form = True
+
+    # ---- (1)
+    shard_check = "skipped (uneven shards)"
+    if n % world == 0:
+        full_sc = torch.empty((n, 4), dtype=torch.int64, device="cuda")
+        dist.all_gather_into_tensor(full_sc, sc)
+        if rank == 0:
+            full_bases = torch.empty((n, 12), dtype=torch.int64, device="cuda")
+            L.check(lib.b381_g1_point_series(L.ptr(g), L.ptr(g), C.c_uint64(n), L.ptr(full_bases), None), "point_series")
+            res = np.zeros(18, dtype=np.uint64)
+            L.check(lib.b381_g1_msm(L.ptr(full_sc), L.ptr(full_bases), n, C.byref(dev_cfg), L.ptr(res)), "single-GPU msm")
+            shard_check = "ok (sharded result == single-GPU MSM of all points on rank 0, bytes)" \
+                if res.tobytes() == result["r"].tobytes() == result["e2e"].tobytes() else "MISMATCH"
+            del full_bases
+        del full_sc
+        torch.cuda.empty_cache()
+
+    # ---- (2)
+    log_d = args.dist_ntt_log
+    nd, loc = 1 << log_d, (1 << log_d) // world
+    ctx = M.GpuNttContext(log_d, device_id=local_rank)
+    dn = D.DistributedNtt(log_d)
+    ok = True
+    for direction in (0, 1):
+        x = canonical_fr(torch, nd, 0x26)                     # same vector on every rank
+        work = D.column_block_of(x, log_d, rank, world).contiguous()
+        rows = dn.forward(work, direction)
+        ctx.ntt_on_device(x.data_ptr(), direction, size=nd, ordering=M.ntt.kNR)
+        ok = ok and bool(torch.equal(rows.reshape(-1, 4), x[rank * loc:(rank + 1) * loc]))
+        del x, rows
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+
+    def ntt_step(marks=None):
+        dn.forward(work, 0, marks)
+    for _ in range(2):
+        ntt_step()
+    ms, _, _ = timed(ntt_step, args.steps)
+    ms /= args.steps
+    evs = []
+
+    def mark(_label):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        evs.append(e)
+    barrier()
+    ntt_step(mark)
+    barrier()
+    ph = torch.tensor([evs[i].elapsed_time(evs[i + 1]) for i in range(3)], device="cuda")
+    dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+    sh = dn.shape
+    ntt_dist = {"metric": f"fr_ntt_2^{log_d}_fourstep_elements_per_s", "value": nd / (ms * 1e-3), "unit": "elements/s",
+                "ms_per_step": ms, "n_gpus": world, "scaling": "strong",
+                "shape": f"[2^{sh['a']}][2^{sh['lo']}], {sh['L']} columns then {sh['rows_per_rank']} rows per GPU",
+                "phases_ms": {"columns": round(float(ph[0]), 4), "all_to_all+transpose": round(float(ph[1]), 4),
+                              "rows": round(float(ph[2]), 4)},
+                "exchange_bytes_per_gpu": loc * 32 * (world - 1) // world,
+                "result_check": "ok (every rank's row block == its single-GPU kNR transform, forward and inverse)"
+                if int(flag.item()) == 1 else "MISMATCH"}
+    del work
+    torch.cuda.empty_cache()
+
+    # ---- (3)
+    nb, nk = 8, 1 << 22
+    bases_k = torch.empty((nk, 12), dtype=torch.int64, device="cuda")
+    L.check(lib.b381_g1_point_series(L.ptr(g), L.ptr(g), C.c_uint64(nk), L.ptr(bases_k), None), "point_series")
+    mine = list(range(rank, nb, world))
+
+    def run_commits(ids):
+        if not ids:
+            return np.zeros((0, 18), dtype=np.uint64)
+        scal = torch.stack([canonical_fr(torch, nk, 0xC0 + j) for j in ids]).contiguous()
+        cfg = lib.b381_default_msm_config()
+        cfg.are_scalars_on_device = cfg.are_points_on_device = True
+        cfg.are_scalars_montgomery_form = cfg.are_points_montgomery_form = True
+        cfg.batch_size, cfg.are_points_shared_in_batch = len(ids), True
+        res = np.zeros((len(ids), 18), dtype=np.uint64)
+
+        def go():
+            L.check(lib.b381_g1_msm(L.ptr(scal), L.ptr(bases_k), nk, C.byref(cfg), L.ptr(res)), "commit batch")
+            return res
+        return go
+
+    go = run_commits(mine)
+    gathered = {}
+
+    def commit_step():
+        part = torch.from_numpy(go().view(np.int64)).cuda() if mine else torch.zeros((0, 18), dtype=torch.int64, device="cuda")
+        if nb % world == 0:
+            allr = torch.empty((nb, 18), dtype=torch.int64, device="cuda")
+            dist.all_gather_into_tensor(allr, part)
+            gathered["r"] = allr
+    commits = None
+    if nb % world == 0:
+        commit_step()
+        k = max(1, args.steps // 2)
+        cms, _, _ = timed(commit_step, k)
+        cms /= k
+        check = None
+        if rank == 0:
+            alone = run_commits(list(range(nb)))().copy()
+            got = gathered["r"].cpu().numpy().view(np.uint64).reshape(world, nb // world, 18)
+            same = all(got[j % world, j // world].tobytes() == alone[j].tobytes() for j in range(nb))
+            check = "ok (== the same 8 commits run on rank 0 alone, bytes)" if same else "MISMATCH"
+        commits = {"metric": "plonk_k22_commit_round_points_per_s", "value": nb * nk / (cms * 1e-3), "unit": "points/s",
+                   "ms_per_step": cms, "batch": nb, "log_n": 22, "n_gpus": world, "scaling": "strong",
+                   "sharding": "commits dealt round-robin, bases replicated, results all_gather'ed", "result_check": check}
+    return shard_check, ntt_dist, commits
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -339,6 +472,12 @@ def main():
               "phases_ms": [round(statistics.mean(c), 4) for c in zip(*g2_phases)][:8], "result": res2}
         del bases2
 
+    # ---- N > 1 only: the exchanges of BASELINE.json configs 3 and 5 on real NCCL
+    shard_check, ntt_dist, commits = None, None, None
+    if world > 1:
+        shard_check, ntt_dist, commits = multi_gpu_legs(args, torch, dist, np, M, L, D, lib, rank, world, local_rank, n, sc, result,
+                                                        timed, barrier)
+
     out = None
     if rank == 0:
         v, ms = C.c_double(), C.c_float()
@@ -431,7 +570,8 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "ntt": ntt,
             "g2": None if g2 is None else {k: v for k, v in g2.items() if k != "result"},
             "probes": {"imad_wide_mad_per_s": imad_peak, "fq_mul_per_s": fq_rate, "fr_mul_per_s": fr_rate},
-            "result_check": check,
+            "result_check": check if world == 1 else shard_check,
+            "ntt_fourstep": ntt_dist, "plonk_commit_round": commits,
         }
     if sampler:
         sampler.stop()

@@ -135,20 +135,27 @@ class DistributedNtt:
         cfg.are_inputs_on_device = cfg.are_outputs_on_device = True
         L.check(self._lib.b381_ntt(L.ptr(data), size, direction, C.byref(cfg), L.ptr(data)), "ntt rows")
 
-    def forward(self, local, direction: int = 0):
+    def forward(self, local, direction: int = 0, marks=None):
+        """`marks`, if given, is called with a label at the boundaries columns | exchange | rows (bench.py records
+        CUDA events there)."""
         import torch.distributed as dist
+        mark = marks or (lambda _label: None)
         if self.world == 1:
             self._rows(local, 1 << self.log_n, 1, direction, 1)        # kNR
             return local
         sh = self.shape
+        mark("begin")
         L.check(self._lib.b381_ntt_dist_columns(L.ptr(local), self.log_n, sh["log_g"], self.rank, sh["a"], direction, None),
                 "ntt_dist_columns")
+        mark("columns")
         rows = exchange_rows(local, self.log_n, self.world,
                              lambda recv, send: dist.all_to_all_single(recv, send, group=self.group))
+        mark("exchange")
         self._rows(rows, 1 << sh["lo"], sh["rows_per_rank"], direction, 1)
         if direction == 1:
             # the row transforms scaled by 2^-lo; the remaining 2^-a is one scalar multiplication
             self._scale_pow2_inv(rows, sh["a"])
+        mark("rows")
         return rows
 
     def _scale_pow2_inv(self, data, a: int):
