@@ -23,6 +23,13 @@ def timings():
     return [round(buf[i], 3) for i in range(k)]
 
 
+def level0():
+    f, b = C.c_float(), C.c_float()
+    if lib.b381_msm_last_level0_ms(C.byref(f), C.byref(b)) == 1:
+        return f"L0 fwd {f.value:.2f} bwd {b.value:.2f}"
+    return ""
+
+
 def main():
     sizes = [int(x) for x in argv[1].split(",")] if len(argv) > 1 else [20, 22]
     lv = argv[2].split(",") if len(argv) > 2 else ["0", "d"]
@@ -44,7 +51,7 @@ def main():
             got, dt = G.run_msm("g1", sc, dev, n)
             got, dt = G.run_msm("g1", sc, dev, n)
             print(f"g1 msm 2^{logn} levels={l}: {'OK' if got == exp else 'MISMATCH'} wall {dt*1e3:.2f} ms  "
-                  f"phases(ms) {timings()}  -> {n/dt:.3e} pts/s", flush=True)
+                  f"phases(ms) {timings()} {level0()} -> {n/dt:.3e} pts/s", flush=True)
         del dev
         torch.cuda.empty_cache()
     print("ALL DONE")
