@@ -148,6 +148,68 @@ def mont_mul_body(b: Block, f: FieldSpec, a: list, bb: list, outs: list[str]):
     final_sub(b, f, r, outs)
 
 
+def mont_sqr_body(b: Block, f: FieldSpec, a: list, outs: list[str]):
+    """a^2 * R^-1 with every off-diagonal product taken ONCE: row i multiplies a[i] by
+        c^(i) = [ a[i],  (a[i+1] << 1),  d[i+2], ..., d[n-1] ]      (limbs i .. n-1; nothing below i)
+    where d = limbs of 2a, so row i contributes a[i]^2 + 2 a[i] * (limbs above i) and the rows sum to a^2.
+    n(n+1)/2 products instead of n^2 (Fq: 78 instead of 144; with the reduction 222 instead of 288 wide
+    multiply-adds); the skipped pairs of a row turn into plain carry propagation on the ALU pipe.  Same two
+    accumulators and renaming as mont_mul_body.  The running value is < 2a + m, which must stay below
+    2^(32n): true for Fq (2^382 + 2^381), NOT for Fr (2r + r > 2^256) -- Fr keeps mul(a, a)."""
+    n = f.n
+    assert 2 * (f.m - 1) + f.m < (1 << (32 * n)), "accumulator bound of the one-sided squaring"
+    d = [None] * n
+    e = [None] * n
+    for j in range(1, n):
+        e[j] = b.op3("shl.b32", a[j], 1)
+        d[j] = b.op4("shf.l.wrap.b32", a[j - 1], a[j], 1)
+
+    def c(i, j):
+        return a[j] if j == i else (e[j] if j == i + 1 else d[j])
+
+    E = [None] * n
+    O = [None] * n
+    for j in range(0, n, 2):
+        E[j] = b.op3("mul.lo.u32", c(0, j), a[0])
+        E[j + 1] = b.op3("mul.hi.u32", c(0, j), a[0])
+    for j in range(1, n, 2):
+        O[j - 1] = b.op3("mul.lo.u32", c(0, j), a[0])
+        O[j] = b.op3("mul.hi.u32", c(0, j), a[0])
+    reduce_step(b, f, E, O)
+    for i in range(1, n):
+        Eo, Oo = E, O
+        E = list(Oo)
+        O = [None] * n
+        E[0] = b.op3("add.cc.u32", E[0], Eo[1])
+        for j in range(1, n, 2):
+            if j < i:                                   # no product in this row: carry propagation only
+                O[j - 1] = b.op3("addc.cc.u32", Eo[j + 1], 0)
+                O[j] = b.op3("addc.cc.u32", Eo[j + 2], 0)
+            elif j < n - 1:
+                O[j - 1] = b.op4("madc.lo.cc.u32", c(i, j), a[i], Eo[j + 1])
+                O[j] = b.op4("madc.hi.cc.u32", c(i, j), a[i], Eo[j + 2])
+            else:
+                O[j - 1] = b.op4("madc.lo.cc.u32", c(i, j), a[i], 0)
+                O[j] = b.op4("madc.hi.u32", c(i, j), a[i], 0)
+        first = True
+        for j in range(0, n, 2):
+            if j < i:
+                continue
+            lo = "mad.lo.cc.u32" if first else "madc.lo.cc.u32"
+            E[j] = b.op4(lo, c(i, j), a[i], E[j])
+            E[j + 1] = b.op4("madc.hi.cc.u32", c(i, j), a[i], E[j + 1])
+            first = False
+        if not first:
+            O[n - 1] = b.op3("addc.u32", O[n - 1], 0)
+        reduce_step(b, f, E, O)
+    r = [None] * n
+    r[0] = b.op3("add.cc.u32", O[0], E[1])
+    for k in range(1, n - 1):
+        r[k] = b.op3("addc.cc.u32", O[k], E[k + 1])
+    r[n - 1] = b.op3("addc.u32", O[n - 1], 0)
+    final_sub(b, f, r, outs)
+
+
 def add_body(b: Block, f: FieldSpec, a, bb, outs):
     n = f.n
     s = []
@@ -198,7 +260,10 @@ def build(f: FieldSpec, op: str) -> Block:
     if op == "mul":
         mont_mul_body(b, f, a, bb, outs)
     elif op == "sqr":
-        mont_mul_body(b, f, a, a, outs)
+        if 2 * (f.m - 1) + f.m < (1 << (32 * n)):
+            mont_sqr_body(b, f, a, outs)
+        else:
+            mont_mul_body(b, f, a, a, outs)
     elif op == "add":
         add_body(b, f, a, bb, outs)
     elif op == "sub":

@@ -41,9 +41,21 @@ def test_mul_with_degenerate_limbs(f):
     for _ in range(150):
         limbs = [rnd.choice((0, 0, 0xFFFFFFFF, 0xFFFFFFFF, 1, rnd.getrandbits(32))) for _ in range(f.n)]
         vals.append(sum(l << (32 * k) for k, l in enumerate(limbs)) % f.m)
+    sqr = G.build(f, "sqr")
     for i, a in enumerate(vals):
         for b in (vals[(5 * i + 1) % len(vals)], a, rnd.randrange(f.m)):
             assert G.run_block(mul, f, a, b) == a * b * rinv % f.m, (hex(a), hex(b))
+        # Fq's one-sided squaring (mont_sqr_body): the doubled limbs and the carry-only pairs see all-0 / all-1 limbs
+        assert G.run_block(sqr, f, a) == a * a * rinv % f.m, hex(a)
+
+
+def test_fq_squaring_takes_each_cross_product_once():
+    """78 + 144 wide multiply-adds (+ 12 m_i) instead of 288: the IMAD-pipe saving the squaring exists for."""
+    def wide(blk):
+        c = blk.count()
+        return sum(v for k, v in c.items() if ".hi" in k)          # one IMAD.WIDE per lo/hi pair
+    assert wide(G.build(G.FQ, "mul")) == 288 and wide(G.build(G.FQ, "sqr")) == 222
+    assert wide(G.build(G.FR, "sqr")) == wide(G.build(G.FR, "mul"))  # Fr: accumulator bound fails, stays mul(a, a)
 
 
 def test_fr_known_answers():
