@@ -520,7 +520,7 @@ static int precompute_entry(const affine_t<F>* in, int bases_size, const b381_ms
       if ((e = sc.alloc(&d_out, (size_t)n * factor)) != cudaSuccess) return map_cuda_error(e);
     }
     uint32_t bits = cfg->bitsize > 0 ? (uint32_t)cfg->bitsize : 255u;
-    uint32_t c = cfg->c > 0 ? (uint32_t)cfg->c : pick_window(n, bits, factor);
+    uint32_t c = cfg->c > 0 ? (uint32_t)cfg->c : pick_window(n, bits, factor, sizeof(F) == sizeof(fq_t));
     const msm_shape sh = make_msm_shape(n, c, bits, factor);
     uint32_t shift = c * sh.Wf;
     if (n) k_precompute_bases<F><<<grid_for(n, 64), 64, 0, st>>>(d_in, d_out, n, factor, shift);
