@@ -35,17 +35,43 @@ template <> struct pair_batch<fq2_t> { static constexpr int B = 16, M = 32; };
 enum : uint32_t { PAIR_NONE = 0xFFFFFFFFu, PAIR_SINGLE = 0x80000000u };
 enum : int { PK_COPY_P = 0, PK_COPY_Q = 1, PK_INF = 2, PK_ADD = 3, PK_DBL = 4 };
 
+// 256-bit global loads (LDG.E.256, new on sm_100) for the point gathers: a 96-byte G1 point is 3 requests instead
+// of 6, its x-coordinate 2 instead of 3.  The level-0 forward pass is bound by the RATE of divergent line requests
+// (every lane of a load instruction hits its own 128-byte line; profiles/r01b_msm_levels_sweep.txt), not by bytes.
+// Needs 32-byte alignment of the element (cudaMalloc'ed point arrays: 96- and 192-byte points keep it); anything
+// else takes the plain path.  Read-only data within the kernel, so the non-coherent path is legal.
+template <class T>
+B381_DI T load_wide(const T* p) {
+#if defined(__CUDA_ARCH__) && !defined(B381_NO_WIDE_LD)
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+    T r;
+    uint64_t* w = reinterpret_cast<uint64_t*>(&r);
+    const char* a = reinterpret_cast<const char*>(p);
+    constexpr int N32 = (int)(sizeof(T) / 32);
+#pragma unroll
+    for (int i = 0; i < N32; i++)
+      asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];"
+                   : "=l"(w[4 * i]), "=l"(w[4 * i + 1]), "=l"(w[4 * i + 2]), "=l"(w[4 * i + 3]) : "l"(a + 32 * i));
+    if (sizeof(T) % 32)
+      asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(w[4 * N32]), "=l"(w[4 * N32 + 1]) : "l"(a + 32 * N32));
+    return r;
+  }
+#endif
+  return *p;
+}
+
 // point at sorted position `pos` of the current level; level 0 gathers through the sorted
 // (index, sign) entries and applies the sign
 template <class F, bool L0>
 B381_DI affine_t<F> pair_load(uint32_t pos, const uint32_t* svals, const affine_t<F>* pts) {
   if (L0) {
     uint32_t v = svals[pos];
-    affine_t<F> p = pts[v >> 1];
+    affine_t<F> p = load_wide(pts + (v >> 1));
     if ((v & 1) && !is_inf(p)) p.y = neg(p.y);
     return p;
   }
-  return pts[pos];
+  return load_wide(pts + pos);
 }
 
 // what P + Q needs, and the denominator that goes into the batched inversion
@@ -129,9 +155,9 @@ template <class F, bool L0>
 B381_DI F pair_load_x(uint32_t pos, const uint32_t* svals, const affine_t<F>* pts, const xrec_t<F>* xs = nullptr) {
   if (L0) {
     uint32_t i = svals[pos] >> 1;
-    return xs ? xs[i].x : pts[i].x;
+    return xs ? xs[i].x : load_wide(&pts[i].x);
   }
-  return pts[pos].x;
+  return load_wide(&pts[pos].x);
 }
 
 // Forward: pre[k*pstride] = product of the denominators before k; returns the product of all B.

@@ -97,12 +97,13 @@ static void launch_level(const uint32_t* in_off, const uint32_t* out_off, uint32
   }
 }
 
-// A level pays once there are enough pairs to fill the GPU (each level has ~0.25 ms of fixed latency: three
-// launches and one thread-serial inversion) and buckets are still long.  Measured on B200: 2^20 points -> 2
-// levels, 2^22 -> 4, 2^24 -> 6 (gpurun sweep, profiles/r01b_msm_levels_sweep.txt).
+// A level pays once there are enough pairs to fill the GPU (each level has ~0.2 ms of fixed latency: three
+// launches and one thread-serial inversion) and buckets are still long.  Measured on B200 (gpurun sweep of
+// B381_MSM_LEVELS, profiles/r01c_msm_levels_sweep.txt): 2^18 points -> 1 level, 2^20 -> 3, 2^21 -> 4, 2^22 -> 5,
+// 2^24 -> 6 or 7 (equal), i.e. levels down to 2^21 pair sums.
 int msm_pair_levels(double avg, size_t total) {
   int levels = 0;
-  while (levels < 8 && avg >= 8.0 && total / 2 >= ((size_t)1 << 22)) { levels++; avg *= 0.5; total /= 2; }
+  while (levels < 8 && avg >= 8.0 && total / 2 >= ((size_t)1 << 21)) { levels++; avg *= 0.5; total /= 2; }
   return levels;
 }
 
