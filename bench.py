@@ -8,6 +8,9 @@ One JSON line on rank 0 (contract in the task statement / DESIGN.md "Measurement
   * step      = one G1 MSM over 2^24 resident bases with Montgomery scalars (BASELINE.json config 3),
                 strong-scaled by contiguous point ranges at N > 1 (one XYZZ partial per GPU, NCCL
                 all_gather, combine); the NTT 2^24 is timed right after it and reported under "ntt".
+                At N > 1 the line also carries "ntt_fourstep" (Fr NTT 2^26 over the N GPUs, ONE NCCL all_to_all) and
+                "plonk_commit_round" (8 MSMs of 2^22 dealt to the ranks), each checked byte for byte against the
+                single-GPU result; "result_check" is then sharded MSM == single-GPU MSM (multi_gpu_legs).
   * value     = points/s with scalars already in HBM;  e2e = same through the public API with HOST
                 (pinned) scalars, H2D inside the timed region, result read back to the host.
   * roofline  = bucket accumulation (affine pre-reduction levels + k_msm_accumulate) against the IMAD.WIDE issue
@@ -516,8 +519,8 @@ def main():
                     "name": "k_msm_pair_bwd<fq_t, 32, level 0>", "kernel_ms": ph[9], "share_of_step": ph[9] / ms_step,
                     "achieved": pairs * 1500.0 / (ph[9] * 1e-3) / 1e9, "unit": "GMAD/s", "frac": pairs * 1500.0 / (ph[9] * 1e-3) / imad_peak,
                     "note": "carry-chain IMAD.WIDE.X issues at ~0.57 of the plain IMAD.WIDE peak used as denominator (profiles/r01_imad_variants.txt)",
-                    "traffic": 73.5e9 * (n_loc / float(1 << 24)),
-                    "traffic_source": "dram__bytes_read+write of this kernel at n = 2^24, ncu --set full (profiles/r01b_pair_kernels_key_metrics.txt), scaled by n",
+                    "traffic": 73.65e9 * (n_loc / float(1 << 24)),
+                    "traffic_source": "dram__bytes_read+write of this kernel at n = 2^24, ncu --set full (profiles/r01c_pair_kernels_key_metrics.txt), scaled by n",
                     "level0_fwd_ms": ph[8]}
         if ntt:
             # n/2 * log2(n) butterflies, one Fr Montgomery product (2*8^2+8 = 136 multiply-adds) each
