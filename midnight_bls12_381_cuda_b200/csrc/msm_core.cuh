@@ -115,17 +115,25 @@ B381_DI void msm_digits_body(uint32_t i, const fr_t* scalars, bool scalars_mont,
 // sorted keys -> offsets[0..nbuckets]; offsets[b] = first position with key >= b; offsets[nbuckets] = total.
 // n_local != 0: the keys are in-window keys, sorted per window slice of n_local entries; the bucket slot of
 // position j is (j / n_local) * Bs + key, which is monotone over the concatenated slices.
+// position j of the sorted keys, whose neighbours j-1 / j belong to windows w_prev / w_cur (per-window sort: keys
+// are in-window, the bucket-set base w * Bs is added here; 0 otherwise)
+B381_DI void msm_offsets_core(size_t j, uint32_t w_prev, uint32_t w_cur, const uint32_t* sorted_keys, size_t total,
+                              uint32_t nbuckets, uint32_t* offsets, uint32_t Bs) {
+  if (j > total) return;
+  uint32_t kp = 0, kc = 0;
+  if (j > 0) kp = sorted_keys[j - 1] + w_prev * Bs;
+  if (j < total) kc = sorted_keys[j] + w_cur * Bs;
+  uint32_t prev = (j == 0) ? 0u : kp + 1u;          // first key not yet started
+  uint32_t cur = (j == total) ? nbuckets + 1u : kc + 1u; // one past this key
+  // every bucket id in [prev, cur) starts at position j
+  for (uint32_t b = prev; b < cur && b <= nbuckets; b++) offsets[b] = (uint32_t)j;
+}
 B381_DI void msm_offsets_body(size_t j, const uint32_t* sorted_keys, size_t total, uint32_t nbuckets,
                               uint32_t* offsets, uint32_t n_local = 0, uint32_t Bs = 0) {
   if (j > total) return;
-  uint32_t kp = 0, kc = 0;
-  if (j > 0) kp = sorted_keys[j - 1] + (n_local ? (uint32_t)((j - 1) / n_local) * Bs : 0u);
-  if (j < total) kc = sorted_keys[j] + (n_local ? (uint32_t)(j / n_local) * Bs : 0u);
-  uint32_t prev = (j == 0) ? 0u : kp + 1u;          // first key not yet started
-  uint32_t cur = (j == total) ? nbuckets + 1u : kc + 1u; // one past this key
-  if (j == 0) prev = 0;
-  // every bucket id in [prev, cur) starts at position j
-  for (uint32_t b = prev; b < cur && b <= nbuckets; b++) offsets[b] = (uint32_t)j;
+  const uint32_t wp = (n_local && j > 0) ? (uint32_t)((j - 1) / n_local) : 0u;
+  const uint32_t wc = n_local ? (uint32_t)(j / n_local) : 0u;
+  msm_offsets_core(j, wp, wc, sorted_keys, total, nbuckets, offsets, n_local ? Bs : 0u);
 }
 
 // ---------------------------------------------------------------- 4 tasks
