@@ -418,7 +418,10 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   tm.mark();
 
   // -- 7 segments, 8 tree
-  uint32_t L = 32;
+  // segment length: measured on B200 (gpurun sweep of B381_MSM_L = 4..64): 32 up to 2^14 buckets per window
+  // (2^21 points: 0.73 ms vs 0.97 at 64, 0.94 at 16), 64 at 2^15 (2^24 points: 1.23 ms vs 1.43) where the kernel is
+  // throughput- rather than latency-bound and the per-segment scalar multiplication is amortised over more buckets
+  uint32_t L = sh.B >= (1u << 15) ? 64 : 32;
   {
     const char* e = getenv("B381_MSM_L");
     if (e && atoi(e) > 0) L = (uint32_t)atoi(e);

@@ -161,6 +161,27 @@ def test_affine_prereduction_levels(cuda, b381, oracle, monkeypatch, levels):
     assert raw_msm(b381, "g2", sc2, bases2, n2, c=5).tobytes() == oracle.msm(2, sc2, bases2).tobytes()
 
 
+@pytest.mark.parametrize("shift", [0, 8, 16])
+def test_device_bases_alignment(cuda, b381, oracle, monkeypatch, shift):
+    """The affine levels fetch points with 256-bit loads when the element is 32-byte aligned (msm_batch.cuh load_wide) and
+    with plain loads otherwise: resident bases handed over at a device address that is only 8- or 16-byte aligned must
+    give the same bytes (G1 and G2, levels forced on at a small size)."""
+    import torch
+    monkeypatch.setenv("B381_MSM_LEVELS", "3")
+    for group, n, words in ((1, 3000, 12), (2, 500, 24)):
+        bases = oracle.gen_series(group, [9, 1, 0, 0], [5, 0, 7, 0], n)
+        sc = oracle.random_fr(400 + shift + group, n)
+        exp = oracle.msm(group, sc, bases).tobytes()
+        buf = torch.zeros(n * words + 4, dtype=torch.int64, device="cuda")
+        assert buf.data_ptr() % 32 == 0
+        view = buf[shift // 8: shift // 8 + n * words]
+        view.copy_(torch.from_numpy(bases.view(np.int64).reshape(-1)))
+        assert view.data_ptr() % 32 == shift
+        d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
+        got = raw_msm(b381, "g1" if group == 1 else "g2", d_sc, view, n, c=6, scalars_on_device=True, points_on_device=True)
+        assert got.tobytes() == exp, (group, shift)
+
+
 @pytest.mark.parametrize("levels", ["", "0", "3"])
 def test_skewed_scalar_distributions(cuda, b381, oracle, monkeypatch, levels):
     """All scalars equal (commitment to a constant vector; the reference's "sum of ones" identity,
