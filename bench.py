@@ -190,46 +190,54 @@ def multi_gpu_legs(args, torch, dist, np, M, L, D, lib, rank, world, local_rank,
     log_d = args.dist_ntt_log
     nd, loc = 1 << log_d, (1 << log_d) // world
     ctx = M.GpuNttContext(log_d, device_id=local_rank)
-    dn = D.DistributedNtt(log_d)
-    ok = True
-    for direction in (0, 1):
-        x = canonical_fr(torch, nd, 0x26)                     # same vector on every rank
-        work = D.column_block_of(x, log_d, rank, world).contiguous()
-        rows = dn.forward(work, direction)
-        ctx.ntt_on_device(x.data_ptr(), direction, size=nd, ordering=M.ntt.kNR)
-        ok = ok and bool(torch.equal(rows.reshape(-1, 4), x[rank * loc:(rank + 1) * loc]))
-        del x, rows
-    flag = torch.tensor([1 if ok else 0], device="cuda")
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    variants = {}
+    for name, fused in (("fused_p2p", True), ("nccl_all_to_all", False)):
+        dn = D.DistributedNtt(log_d, fused=fused)
+        ok = True
+        for direction in (0, 1):
+            x = canonical_fr(torch, nd, 0x26)                     # same vector on every rank
+            work = D.column_block_of(x, log_d, rank, world).contiguous()
+            rows = dn.forward(work, direction)
+            ctx.ntt_on_device(x.data_ptr(), direction, size=nd, ordering=M.ntt.kNR)
+            ok = ok and bool(torch.equal(rows.reshape(-1, 4), x[rank * loc:(rank + 1) * loc]))
+            del x, rows
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 
-    def ntt_step(marks=None):
-        dn.forward(work, 0, marks)
-    for _ in range(2):
-        ntt_step()
-    ms, _, _ = timed(ntt_step, args.steps)
-    ms /= args.steps
-    evs = []
+        def ntt_step(marks=None):
+            dn.forward(work, 0, marks)
+        for _ in range(2):
+            ntt_step()
+        ms, _, _ = timed(ntt_step, args.steps)
+        ms /= args.steps
+        evs = []
 
-    def mark(_label):
-        e = torch.cuda.Event(enable_timing=True)
-        e.record()
-        evs.append(e)
-    barrier()
-    ntt_step(mark)
-    barrier()
-    ph = torch.tensor([evs[i].elapsed_time(evs[i + 1]) for i in range(3)], device="cuda")
-    dist.all_reduce(ph, op=dist.ReduceOp.MAX)
-    sh = dn.shape
+        def mark(_label):
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            evs.append(e)
+        barrier()
+        ntt_step(mark)
+        barrier()
+        ph = torch.tensor([evs[i].elapsed_time(evs[i + 1]) for i in range(3)], device="cuda")
+        dist.all_reduce(ph, op=dist.ReduceOp.MAX)
+        variants[name] = (ms, [round(float(v), 4) for v in ph], int(flag.item()) == 1, dn.fused)
+        sh = dn.shape
+        del work
+        torch.cuda.empty_cache()
+    ms, ph, ok_f, was_fused = variants["fused_p2p"]
+    ms_n, ph_n, ok_n, _ = variants["nccl_all_to_all"]
     ntt_dist = {"metric": f"fr_ntt_2^{log_d}_fourstep_elements_per_s", "value": nd / (ms * 1e-3), "unit": "elements/s",
                 "ms_per_step": ms, "n_gpus": world, "scaling": "strong",
                 "shape": f"[2^{sh['a']}][2^{sh['lo']}], {sh['L']} columns then {sh['rows_per_rank']} rows per GPU",
-                "phases_ms": {"columns": round(float(ph[0]), 4), "all_to_all+transpose": round(float(ph[1]), 4),
-                              "rows": round(float(ph[2]), 4)},
+                "exchange": "fused into the last column pass: stores go to the owning GPU's row buffer over NVLink peer memory "
+                            "(b381_ntt_dist_columns_p2p), two 4-byte all_reduce barriers" if was_fused else "NCCL all_to_all",
+                "phases_ms": {"barrier+columns(+remote stores)": ph[0], "barrier": ph[1], "rows": ph[2]},
+                "nccl_all_to_all_variant": {"ms_per_step": ms_n, "value": nd / (ms_n * 1e-3),
+                                            "phases_ms": {"columns": ph_n[0], "all_to_all+transpose": ph_n[1], "rows": ph_n[2]}},
                 "exchange_bytes_per_gpu": loc * 32 * (world - 1) // world,
-                "result_check": "ok (every rank's row block == its single-GPU kNR transform, forward and inverse)"
-                if int(flag.item()) == 1 else "MISMATCH"}
-    del work
-    torch.cuda.empty_cache()
+                "result_check": "ok (every rank's row block == its single-GPU kNR transform, forward and inverse, both variants)"
+                if ok_f and ok_n else f"MISMATCH (fused ok={ok_f}, nccl ok={ok_n})"}
 
     # ---- (3)
     nb, nk = 8, 1 << 22

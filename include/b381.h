@@ -241,6 +241,19 @@ int b381_g2_msm_partial(const b381_fr* scalars, const b381_g2_affine* bases, int
  * exchanges row blocks (all-to-all) and finishes with b381_ntt(batch = 2^upper_stages / #GPUs,
  * size = 2^lo, ordering kNR) -- see midnight_bls12_381_cuda_b200/dist.py. */
 int b381_ntt_dist_columns(b381_fr* data_device, int log_n, int log_gpus, int rank, int upper_stages, int dir, void* stream);
+/* Same, with the exchange FUSED into the last column pass: its stores go straight into the row buffers of the
+ * owning GPUs (`peer_rows[r]` = rank r's [2^upper_stages / #GPUs][2^lo] buffer mapped into this process, e.g. with
+ * b381_ipc_alloc / b381_ipc_open), already transposed, so no all-to-all and no transpose pass follow: the caller
+ * only needs a barrier across ranks before the row transforms (and before the next call reuses the buffers).
+ * At most 8 GPUs.  `data_device` is scratch afterwards. */
+int b381_ntt_dist_columns_p2p(b381_fr* data_device, int log_n, int log_gpus, int rank, int upper_stages, int dir,
+                              void* const* peer_rows, void* stream);
+/* Peer-visible device memory for the call above (one process per GPU): cudaMalloc + its 64-byte CUDA IPC handle;
+ * b381_ipc_open maps a peer's handle into this process (peer access is enabled lazily), b381_ipc_close unmaps it;
+ * the owner releases the allocation with b381_free. */
+int b381_ipc_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
+int b381_ipc_open(const unsigned char handle[64], void** ptr);
+int b381_ipc_close(void* ptr);
 /* Adds `count` XYZZ partials (device) and writes ONE ICICLE standard-form projective result. */
 int b381_g1_msm_combine(const void* partials_xyzz_device, int count, void* stream, bool result_on_device,
                         b381_g1_projective* result);

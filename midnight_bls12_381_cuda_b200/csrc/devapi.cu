@@ -1,5 +1,7 @@
 // Device plumbing behind the C ABI: pure CUDA-runtime forwarding, no kernels.
 // Mirrors what CudaDeviceAPI offers ICICLE (bls12-381/src/device/cuda_device_api.cu:38-149).
+#include <cstring>
+
 #include "common.cuh"
 
 using namespace b381;
@@ -28,5 +30,25 @@ int b381_stream_create(void** s) {
 int b381_stream_destroy(void* s) { return cudaStreamDestroy((cudaStream_t)s) == cudaSuccess ? B381_SUCCESS : B381_STREAM_DESTRUCTION_FAILED; }
 int b381_stream_synchronize(void* s) { return cudaStreamSynchronize((cudaStream_t)s) == cudaSuccess ? B381_SUCCESS : B381_SYNCHRONIZATION_FAILED; }
 int b381_device_synchronize(void) { return cudaDeviceSynchronize() == cudaSuccess ? B381_SUCCESS : B381_SYNCHRONIZATION_FAILED; }
+// Peer-visible device buffers for the fused exchange of the four-step NTT (one process per GPU): a plain cudaMalloc
+// allocation, its 64-byte IPC handle for the other ranks, and the mapping of a peer's handle into this process.
+int b381_ipc_alloc(size_t bytes, void** ptr, unsigned char handle[64]) {
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  if (!ptr || !handle) return B381_INVALID_POINTER;
+  cudaError_t e = cudaMalloc(ptr, bytes);
+  if (e != cudaSuccess) return map_cuda_error(e);
+  cudaIpcMemHandle_t h;
+  e = cudaIpcGetMemHandle(&h, *ptr);
+  if (e != cudaSuccess) { cudaFree(*ptr); *ptr = nullptr; return map_cuda_error(e); }
+  memcpy(handle, &h, 64);
+  return B381_SUCCESS;
+}
+int b381_ipc_open(const unsigned char handle[64], void** ptr) {
+  if (!ptr || !handle) return B381_INVALID_POINTER;
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  return map_cuda_error(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+}
+int b381_ipc_close(void* ptr) { return map_cuda_error(cudaIpcCloseMemHandle(ptr)); }
 const char* b381_version(void) { return "b381-cuda-b200 0.1 (sm_100a)"; }
 }

@@ -291,11 +291,12 @@ static int ntt_run(const fr_t* input, int size, int dir, const b381_ntt_config* 
 // Step 1 of the distributed (four-step) NTT: the top `a` stages of a 2^log_n transform on this
 // GPU's column block (see ntt_pass_params::dist_*), in place, device memory.
 static int ntt_dist_columns(fr_t* data, uint32_t log_n, uint32_t log_gpus, uint32_t rank, uint32_t a, int dir,
-                            cudaStream_t st) {
+                            cudaStream_t st, void* const* peer_rows = nullptr) {
   if (!data) return B381_INVALID_POINTER;
   if (log_gpus == 0 || a == 0 || a + log_gpus > log_n || rank >= (1u << log_gpus)) return B381_INVALID_ARGUMENT;
   const uint32_t lo = log_n - a;            // global bit where the column index ends
   if (lo < log_gpus + 2) return B381_INVALID_ARGUMENT;   // keep >= 4 adjacent elements per tile row
+  if (peer_rows && log_gpus > 3) return B381_INVALID_ARGUMENT;   // ntt_pass_params::peer_out holds 8 GPUs
   const uint32_t logL = lo - log_gpus;
   const uint32_t n_loc = log_n - log_gpus;
   std::unique_lock<std::mutex> lk(g_dom_mu);
@@ -316,6 +317,14 @@ static int ntt_dist_columns(fr_t* data, uint32_t log_n, uint32_t log_gpus, uint3
     p.inverse = dir == B381_NTT_INVERSE;
     p.twiddles = tw;
     p.dist_shift = log_gpus; p.dist_logL = logL; p.dist_lo = lo; p.dist_lbase = rank << logL;
+    if (peer_rows && i + 1 == np) {
+      p.peer_on = 1;
+      p.peer_logR = a - log_gpus;
+      for (uint32_t r = 0; r < (1u << log_gpus); r++) {
+        if (!peer_rows[r]) return B381_INVALID_POINTER;
+        p.peer_out[r] = (fr_t*)peer_rows[r];
+      }
+    }
     const uint32_t tile_log = p.S + p.g;
     const uint64_t tiles = p.total >> tile_log;
     launch_ntt_pass(p, data, data, (unsigned)tiles, (size_t)2 * sizeof(uint4) << tile_log, st);
@@ -334,6 +343,13 @@ int b381_ntt_dist_columns(b381_fr* data_device, int log_n, int log_gpus, int ran
   if (log_n < 0 || log_gpus < 0 || rank < 0 || upper_stages < 0) return B381_INVALID_ARGUMENT;
   return ntt_dist_columns((fr_t*)data_device, (uint32_t)log_n, (uint32_t)log_gpus, (uint32_t)rank, (uint32_t)upper_stages, dir,
                           (cudaStream_t)stream);
+}
+int b381_ntt_dist_columns_p2p(b381_fr* data_device, int log_n, int log_gpus, int rank, int upper_stages, int dir,
+                              void* const* peer_rows, void* stream) {
+  if (log_n < 0 || log_gpus < 0 || rank < 0 || upper_stages < 0) return B381_INVALID_ARGUMENT;
+  if (!peer_rows) return B381_INVALID_POINTER;
+  return ntt_dist_columns((fr_t*)data_device, (uint32_t)log_n, (uint32_t)log_gpus, (uint32_t)rank, (uint32_t)upper_stages, dir,
+                          (cudaStream_t)stream, peer_rows);
 }
 int b381_ntt_init_domain(const b381_fr* root, const b381_ntt_init_domain_config* cfg) {
   if (!root) return B381_INVALID_POINTER;

@@ -47,6 +47,13 @@ struct ntt_pass_params {
   uint32_t dist_logL;     // log2 of local columns
   uint32_t dist_lo;       // global bit position where the column index ends (= dist_logL + dist_shift)
   uint32_t dist_lbase;    // first global column owned by this GPU
+  // Fused exchange (last column pass only): instead of the local array, element (row i, column l) is stored
+  // straight into the ROW buffer of the GPU that owns row i -- peer memory over NVLink -- at
+  // (i mod R) * 2^dist_lo + l_base + l, i.e. already in the [R][2^lo] layout the row transforms read.
+  // The all_to_all and the transpose pass of the four-step NTT disappear.
+  uint32_t peer_on;
+  uint32_t peer_logR;     // log2 of rows per GPU
+  fr_t* peer_out[8];      // row buffer of every GPU, mapped into this process (CUDA IPC)
 };
 
 // local flat index -> global flat index (identity when not distributed)
@@ -236,6 +243,13 @@ B381_DI void ntt_tile_store(const ntt_pass_params& p, uint64_t tile_id, uint32_t
     v = mul(v, fr_gload_ro(p.post_scale + bitrev32(i, p.n)));
   } else if (p.has_post_const) {
     v = mul(v, p.post_const);
+  }
+  if (p.peer_on) {
+    const uint64_t row = I >> p.dist_logL;
+    const uint32_t l = (uint32_t)(I & ((1ull << p.dist_logL) - 1));
+    fr_t* dst = p.peer_out[row >> p.peer_logR];
+    fr_gstore(dst + (((row & ((1ull << p.peer_logR) - 1)) << p.dist_lo) | (p.dist_lbase + l)), v);
+    return;
   }
   fr_gstore(out + ntt_addr(p, I, p.perm_out != 0), v);
 }

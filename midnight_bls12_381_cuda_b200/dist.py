@@ -4,8 +4,11 @@
 
   * MSM  -- contiguous point ranges, one XYZZ partial (192 B G1 / 384 B G2) per GPU, all_gather of the
             partials, one combine + inversion on every rank (cheap) or rank 0 only.
-  * NTT  -- four-step over column blocks: local upper stages (b381_ntt_dist_columns), ONE all-to-all
-            of row blocks over NVLink, local row NTTs.  Output = global kNR order, block-distributed.
+  * NTT  -- four-step over column blocks: local upper stages whose LAST pass stores straight into the owning
+            GPU's row buffer over NVLink peer memory (b381_ntt_dist_columns_p2p: exchange and transpose fused into
+            the kernel's epilogue), two 4-byte all_reduce barriers, local row NTTs.  The NCCL path (one
+            all_to_all of row blocks + transpose) stays as `fused=False`.  Output = global kNR order,
+            block-distributed.
 
 torch is plumbing here (device buffers + collectives); every field/curve operation happens in the
 CUDA library.  The index arithmetic below is pure host logic and is unit-tested with gloo on CPU
@@ -121,13 +124,47 @@ class DistributedNtt:
     the rank's GPU.  Output: rows [rank*R, (rank+1)*R) of the [2^a][2^lo] matrix whose flat global
     position I holds X[bitrev(I)] -- i.e. the global kNR result, block-distributed."""
 
-    def __init__(self, log_n: int, group=None):
+    def __init__(self, log_n: int, group=None, fused: bool | None = None):
+        """`fused` (default: on for 2..8 GPUs): the last column pass stores straight into the row buffers of the
+        owning GPUs over NVLink peer memory (b381_ntt_dist_columns_p2p), so the all_to_all and the transpose pass
+        are replaced by two 4-byte all_reduce barriers.  `fused=False` keeps the NCCL all_to_all path."""
         import torch.distributed as dist
         self.log_n, self.group = log_n, group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.shape = fourstep_shape(log_n, self.world) if self.world > 1 else None
         self._lib = L.lib()
+        self.fused = (1 < self.world <= 8) if fused is None else (fused and 1 < self.world <= 8)
+        self._peers = None
+
+    def _setup_peers(self):
+        """one peer-visible row buffer per rank (cudaMalloc + CUDA IPC), every rank maps all of them"""
+        import torch
+        import torch.distributed as dist
+        nbytes = self.shape["local"] * 32
+        mine, handle = C.c_void_p(), (C.c_ubyte * 64)()
+        L.check(self._lib.b381_ipc_alloc(C.c_size_t(nbytes), C.byref(mine), handle), "ipc_alloc")
+        handles = [None] * self.world
+        dist.all_gather_object(handles, bytes(handle), group=self.group)
+        self._peers = (C.c_void_p * self.world)()
+        for r, hb in enumerate(handles):
+            if r == self.rank:
+                self._peers[r] = mine.value
+            else:
+                q = C.c_void_p()
+                L.check(self._lib.b381_ipc_open((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(q)), "ipc_open")
+                self._peers[r] = q.value
+        self._flag = torch.zeros(1, device="cuda")
+
+        class _Rows:       # zero-copy torch view of the row buffer
+            __cuda_array_interface__ = {"shape": (self.shape["local"], 4), "typestr": "<i8", "data": (mine.value, False),
+                                        "version": 3, "strides": None}
+        self._rows_view = torch.as_tensor(_Rows(), device="cuda")
+
+    def _barrier(self):
+        """stream-ordered barrier across the ranks (no host synchronisation)"""
+        import torch.distributed as dist
+        dist.all_reduce(self._flag, group=self.group)
 
     def _rows(self, data, size, batch, direction, ordering):
         cfg = self._lib.b381_default_ntt_config()
@@ -144,6 +181,22 @@ class DistributedNtt:
             self._rows(local, 1 << self.log_n, 1, direction, 1)        # kNR
             return local
         sh = self.shape
+        if self.fused:
+            if self._peers is None:
+                self._setup_peers()
+            rows = self._rows_view
+            mark("begin")
+            self._barrier()                # every rank is done with the previous contents of its row buffer
+            L.check(self._lib.b381_ntt_dist_columns_p2p(L.ptr(local), self.log_n, sh["log_g"], self.rank, sh["a"], direction,
+                                                        self._peers, None), "ntt_dist_columns_p2p")
+            mark("columns")
+            self._barrier()                # every rank's column pass, i.e. every remote store, has completed
+            mark("exchange")
+            self._rows(rows, 1 << sh["lo"], sh["rows_per_rank"], direction, 1)
+            if direction == 1:
+                self._scale_pow2_inv(rows, sh["a"])
+            mark("rows")
+            return rows
         mark("begin")
         L.check(self._lib.b381_ntt_dist_columns(L.ptr(local), self.log_n, sh["log_g"], self.rank, sh["a"], direction, None),
                 "ntt_dist_columns")
