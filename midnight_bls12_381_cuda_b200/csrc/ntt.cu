@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(kNttThreads, RMAX == 3 ? 2 : 3) k_ntt_pass(ntt
   const uint32_t tile_elems = 1u << (p.S + p.g + p.x);
   t.lo = smem;
   t.hi = smem + tile_elems;
-  const uint64_t tile_id = blockIdx.x;
+  const uint64_t tile_id = p.tile_rot ? (blockIdx.x + p.tile_rot) % gridDim.x : blockIdx.x;
   for (uint32_t pos = threadIdx.x; pos < tile_elems; pos += blockDim.x) ntt_tile_load(p, tile_id, pos, in, t);
   __syncthreads();
   uint32_t s = p.S;
@@ -327,6 +327,7 @@ static int ntt_dist_columns(fr_t* data, uint32_t log_n, uint32_t log_gpus, uint3
     }
     const uint32_t tile_log = p.S + p.g;
     const uint64_t tiles = p.total >> tile_log;
+    if (p.peer_on) p.tile_rot = (uint32_t)((tiles >> log_gpus) * rank);   // tiles are ordered by destination GPU
     launch_ntt_pass(p, data, data, (unsigned)tiles, (size_t)2 * sizeof(uint4) << tile_log, st);
     hi -= S;
     rest -= S;

@@ -53,6 +53,8 @@ struct ntt_pass_params {
   // The all_to_all and the transpose pass of the four-step NTT disappear.
   uint32_t peer_on;
   uint32_t peer_logR;     // log2 of rows per GPU
+  uint32_t tile_rot;      // CTAs visit the tiles rotated by this much, so that at any moment the GPUs store to
+                          // DIFFERENT peers (rank r starts with its own rows) instead of all hitting GPU 0 first
   fr_t* peer_out[8];      // row buffer of every GPU, mapped into this process (CUDA IPC)
 };
 
@@ -123,6 +125,15 @@ B381_DI fr_t fr_gload_ro(const fr_t* p) {   // read-only path (twiddles, scale t
   return r;
 #else
   return *p;
+#endif
+}
+// one 256-bit store (STG.E.256, sm_100): the peer-memory stores of the fused exchange must not reach NVLink as two
+// half-sector writes per element (measured at 8 GPUs: 16-byte stores made the column pass 2x slower)
+B381_DI void fr_gstore256(fr_t* p, const fr_t& v) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(v.l[0]), "l"(v.l[1]), "l"(v.l[2]), "l"(v.l[3]) : "memory");
+#else
+  *p = v;
 #endif
 }
 B381_DI void fr_gstore(fr_t* p, const fr_t& v) {
@@ -248,7 +259,7 @@ B381_DI void ntt_tile_store(const ntt_pass_params& p, uint64_t tile_id, uint32_t
     const uint64_t row = I >> p.dist_logL;
     const uint32_t l = (uint32_t)(I & ((1ull << p.dist_logL) - 1));
     fr_t* dst = p.peer_out[row >> p.peer_logR];
-    fr_gstore(dst + (((row & ((1ull << p.peer_logR) - 1)) << p.dist_lo) | (p.dist_lbase + l)), v);
+    fr_gstore256(dst + (((row & ((1ull << p.peer_logR) - 1)) << p.dist_lo) | (p.dist_lbase + l)), v);
     return;
   }
   fr_gstore(out + ntt_addr(p, I, p.perm_out != 0), v);
