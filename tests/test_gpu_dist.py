@@ -68,3 +68,33 @@ def test_fourstep_ntt_equals_single_gpu(cuda, b381, oracle, log_n, world):
             outs.append(rows)
         got = cuda.cat(outs)
         assert cuda.equal(got, ref), (log_n, world, direction)
+
+
+@pytest.mark.parametrize("log_n,world", [(12, 2), (16, 4), (18, 8)])
+def test_fourstep_ntt_fused_exchange_equals_single_gpu(cuda, b381, oracle, log_n, world):
+    """b381_ntt_dist_columns_p2p: the last column pass stores straight into the row buffers of the owning ranks
+    (here: `world` buffers in one process standing in for the IPC-mapped peer buffers), 256-bit stores, tile order
+    rotated by rank.  Afterwards every buffer must hold that rank's rows ready for the row transforms."""
+    import midnight_bls12_381_cuda_b200 as M
+    from midnight_bls12_381_cuda_b200 import dist as D
+    lib = b381.lib()
+    ctx = M.GpuNttContext(24)
+    n = 1 << log_n
+    x = oracle.random_fr(log_n * 7 + world, n)
+    sh = D.fourstep_shape(log_n, world)
+    for direction in (0, 1):
+        ref = cuda.from_numpy(x.view(np.int64)).cuda()
+        ctx.ntt_on_device(ref.data_ptr(), direction, size=n, ordering=M.ntt.kNR)
+        rows = [cuda.zeros((sh["local"], 4), dtype=cuda.int64, device="cuda") for _ in range(world)]
+        peers = (C.c_void_p * world)(*[r.data_ptr() for r in rows])
+        for rank in range(world):
+            loc = cuda.from_numpy(np.ascontiguousarray(D.column_block_of(x, log_n, rank, world)).view(np.int64)).cuda()
+            assert lib.b381_ntt_dist_columns_p2p(b381.ptr(loc), log_n, sh["log_g"], rank, sh["a"], direction, peers, None) == 0
+        dn = D.DistributedNtt(log_n)
+        for rank in range(world):
+            dn._rows(rows[rank], 1 << sh["lo"], sh["rows_per_rank"], direction, 1)
+            if direction == 1:
+                dn._scale_pow2_inv(rows[rank], sh["a"])
+        assert cuda.equal(cuda.cat(rows), ref), (log_n, world, direction)
+    # more than 8 GPUs do not fit ntt_pass_params::peer_out
+    assert lib.b381_ntt_dist_columns_p2p(b381.ptr(rows[0]), 20, 4, 0, 10, 0, peers, None) != 0
