@@ -185,11 +185,14 @@ static uint32_t ceil_log2_u64(uint64_t v) {
   return b;
 }
 
-// Window size (replaces get_optimal_c, include/msm.cuh:115-140).  Full-width scalars without precomputed-bases
-// folding use the optimum MEASURED on B200 (gpurun sweep of c = 8..16 at 2^12..2^24, profiles/r01c_msm_window_sweep.txt):
-// the tail (bucket reduction + window combine) is latency- not throughput-bound, so fewer, larger windows win much
-// earlier than a product count predicts -- 2^16: c = 10 -> 4.05 ms, c = 15 -> 2.74 ms; 2^20: c = 16 -> 9.6 ms,
-// c = 15 -> 9.2 ms; from 2^22 up c = 16.  Everything else (short scalars, folded windows) minimises
+// Window size (replaces get_optimal_c, include/msm.cuh:115-140).  Full-width G1 scalars without precomputed-bases
+// folding use the optimum MEASURED on B200 with scalars uniform in [0, r) (gpurun sweep of c = 12..16 at 2^12..2^21,
+// profiles/r01c_msm_window_sweep.txt): c = 13 up to 2^17 points (2^16: 2.80 ms vs 3.24 at c = 16), c = 16 above
+// (2^20: 9.07 ms vs 9.87 at c = 13).  The tail (bucket reduction + window combine) is latency- not throughput-bound,
+// so few large windows win much earlier than a product count predicts.  c = 15 is never the optimum for uniform
+// scalars: 17 windows cover exactly 255 bits, so an 18th window exists only for the signed-digit carry and its single
+// bucket receives 45 % of the points (r >> 240 = 0x73ed > 2^14).  At c = 16 the top digit is at most 0x73ed < 2^15 and
+// never carries.  Everything else (short scalars, folded windows, G2) minimises
 //   W * 10 n  +  Wf * 72 * 2^(c-1)      [Fq-mul equivalents: bucket insertions + bucket reduction]
 // with W = ceil((bits+1)/c), capped at c = 16: beyond that the per-bucket load (n / 2^(c-1)) gets so
 // small that warp divergence in the accumulate kernel eats the saving (measured on B200: 2^24 points,
@@ -197,8 +200,7 @@ static uint32_t ceil_log2_u64(uint64_t v) {
 static uint32_t pick_window(uint32_t n, uint32_t bits, uint32_t factor, bool g1 = true) {
   const char* e = getenv("B381_MSM_C");
   if (e && atoi(e) > 0) return (uint32_t)atoi(e);
-  // (G1 only: at G2 2^20 the 1-bit top window of c = 15 costs more in the heavy-bucket finalize than it saves: 32.8 vs 29.5 ms)
-  if (g1 && factor <= 1 && bits >= 250 && n >= (1u << 11)) return n <= (1u << 15) ? 13u : n < (3u << 20) ? 15u : 16u;
+  if (g1 && factor <= 1 && bits >= 250 && n >= (1u << 11)) return n <= (1u << 17) ? 13u : 16u;
   double best = 1e300;
   uint32_t bc = 4;
   for (uint32_t c = 4; c <= 16; c++) {
