@@ -454,7 +454,10 @@ def main():
                "e2e": None if ntt_e2e is None else {"value": n_loc / (ntt_e2e * 1e-3), "unit": "elements/s",
                                                      "h2d_bytes_per_step": n_loc * 32, "d2h_bytes_per_step": n_loc * 32},
                "roofline": {"bound": "hbm", "achieved": alg_bytes / (ntt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                            "frac": alg_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                            "frac": alg_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak,
+                            # dram__bytes_read+write of the three k_ntt_pass launches of one 2^24 transform, ncu --set full
+                            # (profiles/r01d_ntt_pass_key_metrics.txt: 1.57 + 1.02 + 1.06 GB), per launch average
+                            "traffic": (3.65e9 / 3) if args.log_n == 24 and world == 1 else None,
                             "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                             "kernel": f"k_ntt_pass x{passes}", "note": "compute (IMAD) bound: see imad_frac"},
                "gpu_launches": passes}

@@ -138,6 +138,27 @@ def test_errors_and_domain(ctx, b381, oracle):
     N.GpuNttContext(24)       # restore for later tests
 
 
+@pytest.mark.parametrize("logn", [21, 22, 24])
+def test_natural_order_equals_bit_reversed_order(ctx, oracle, cuda, logn):
+    """Large transforms in both output orders: kNN scatters the last pass's stores to bit-reversed addresses, kNR
+    stores in place.  Same transform, so y_NN[i] == y_NR[bitrev(i)] element for element, forward and inverse."""
+    import midnight_bls12_381_cuda_b200 as M
+    n = 1 << logn
+    a = oracle.random_fr(0xB12381_3000 + logn, n)
+    idx = cuda.arange(n, dtype=cuda.int64, device="cuda")
+    rev = cuda.zeros_like(idx)
+    for b in range(logn):
+        rev |= ((idx >> b) & 1) << (logn - 1 - b)
+    del idx
+    for direction in (M.ntt.FORWARD, M.ntt.INVERSE):
+        nn = cuda.from_numpy(a.view(np.int64)).cuda()
+        nr = nn.clone()
+        ctx.ntt_on_device(nn.data_ptr(), direction, size=n, ordering=M.ntt.kNN)
+        ctx.ntt_on_device(nr.data_ptr(), direction, size=n, ordering=M.ntt.kNR)
+        assert cuda.equal(nn, nr[rev]), (logn, direction)
+        del nn, nr
+
+
 def test_full_size_2_24(ctx, oracle, cuda):
     """2^24: inverse(forward(x)) == x, linearity against a second vector, Horner spot checks."""
     import midnight_bls12_381_cuda_b200 as M
