@@ -147,13 +147,22 @@ class DistributedNtt:
         handles = [None] * self.world
         dist.all_gather_object(handles, bytes(handle), group=self.group)
         self._peers = (C.c_void_p * self.world)()
+        ok = 1
         for r, hb in enumerate(handles):
             if r == self.rank:
                 self._peers[r] = mine.value
-            else:
-                q = C.c_void_p()
-                L.check(self._lib.b381_ipc_open((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(q)), "ipc_open")
-                self._peers[r] = q.value
+                continue
+            q = C.c_void_p()
+            if self._lib.b381_ipc_open((C.c_ubyte * 64).from_buffer_copy(hb), C.byref(q)) != 0:
+                ok = 0                      # no peer access between these two GPUs
+                break
+            self._peers[r] = q.value
+        # every rank must take the same path: one rank without peer access sends all of them to the NCCL exchange
+        agree = torch.tensor([ok], device="cuda")
+        dist.all_reduce(agree, op=dist.ReduceOp.MIN, group=self.group)
+        if int(agree.item()) == 0:
+            self.fused, self._peers = False, None
+            return
         self._flag = torch.zeros(1, device="cuda")
 
         class _Rows:       # zero-copy torch view of the row buffer
@@ -184,6 +193,7 @@ class DistributedNtt:
         if self.fused:
             if self._peers is None:
                 self._setup_peers()
+        if self.fused:
             rows = self._rows_view
             mark("begin")
             self._barrier()                # every rank is done with the previous contents of its row buffer
