@@ -11,13 +11,18 @@ One JSON line on rank 0 (contract in the task statement / DESIGN.md "Measurement
                 At N > 1 the line also carries "ntt_fourstep" (Fr NTT 2^26 over the N GPUs, ONE NCCL all_to_all) and
                 "plonk_commit_round" (8 MSMs of 2^22 dealt to the ranks), each checked byte for byte against the
                 single-GPU result; "result_check" is then sharded MSM == single-GPU MSM (multi_gpu_legs).
-  * value     = points/s with scalars already in HBM;  e2e = same through the public API with HOST
-                (pinned) scalars, H2D inside the timed region, result read back to the host.
+  * value     = points/s with scalars already in HBM;  e2e = the reference-facing plugin call itself
+                (b381_g1_msm, what msm_cuda_impl is replaced by) with HOST (pinned) scalars, are_scalars_on_device =
+                false, synchronous, H2D and the 144-byte result D2H inside the timed region; "e2e_pipelined" = the
+                host API's async calls (msm_with_device_bases_async, one stream each) with two commits in flight.
   * roofline  = bucket accumulation (affine pre-reduction levels + k_msm_accumulate) against the IMAD.WIDE issue
                 peak MEASURED in this run (the path is integer-pipe bound, not HBM/tensor); "ntt.roofline" is the
                 HBM view north_star asks for.
   * cpu_baseline / --impl reference = the CPU port oracle/oracle.c (BLST / midnight-curves are not in
     this image: kind "port") on a bounded sample with every host core.
+  * reference_gpu = the reference's OWN sm_100 kernels (oracle/_ref/libref_field.so, libref_msm.so, compiled from
+    /root/reference where the sources lie) timed on this GPU beside ours through the same signatures -- the R-GPU
+    comparator of SURVEY.md 2.2; outside the product path and outside every timed region of ours.
 The oracle is used here ONLY for that CPU leg and for a one-off result check outside the timed region.
 """
 from __future__ import annotations
@@ -57,6 +62,7 @@ def parse():
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--cpu-log-n", type=int, default=0, help="log2 size of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference's own kernels (oracle/_ref) timed beside ours")
     ap.add_argument("--dist-ntt-log", type=int, default=26, help="log2 size of the four-step NTT timed at N > 1")
     return ap.parse_args()
 
@@ -124,20 +130,34 @@ def cpu_leg(log_n: int, steps: int, warmup: int):
             "ntt_log_n": ntt_log, "ntt_s": ntt_s, "ntt_elems_per_s": (1 << ntt_log) / ntt_s}
 
 
+def workload_config(args, world):
+    """The `config` object of BOTH arms (the driver compares them): what is computed, nothing measured."""
+    return {"workload": f"G1 MSM n=2^{args.log_n}, bases (1+i)G resident in HBM, uniform Montgomery scalars, signed-digit "
+                        f"Pippenger; + Fr NTT 2^{args.log_n} (kNN, in place)",
+            "sharding": f"{world} contiguous point ranges, one XYZZ partial per GPU, NCCL all_gather" if world > 1 else "single GPU",
+            "l2": "inputs (0.5 GiB scalars + 1.5 GiB bases) exceed the 126 MB L2; no flush needed"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers: this arm is the CPU path with EVERY host core, at any N
+    os.environ.pop("OMP_NUM_THREADS", None)
+    from oracle import cref as O
+    O.set_threads(os.cpu_count() or 1)
     log_n = args.cpu_log_n or 18
-    steps, warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     r = cpu_leg(log_n, steps, warmup)
-    sample = f"G1 MSM 2^{log_n} points (of the 2^{args.log_n} workload), {steps} steps; Fr NTT 2^{r['ntt_log_n']}"
+    sample = (f"every step = G1 MSM over 2^{log_n} points of the 2^{args.log_n} workload (oracle/oracle.c, OpenMP, "
+              f"{r['cores']} threads); Fr NTT 2^{r['ntt_log_n']} once")
     line = {
         "impl": "reference", "metric": f"g1_msm_2^{args.log_n}_points_per_s", "value": r["msm_pts_per_s"], "unit": "points/s",
         "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": r["msm_s"] * 1e3, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "u64 (6x64 Fq / 4x64 Fr Montgomery)", "data": "synthetic",
-        "config": {"workload": f"G1 MSM, CPU port of the reference's MIDNIGHT_DEVICE=cpu path (Pippenger, OpenMP), sample 2^{log_n}",
-                   "note": "BLST/midnight-curves are absent from this image (SURVEY.md 8c): oracle/oracle.c stands in"},
+        "scaling": "strong", "vs_baseline": None, "dtype": "u64 (6x64 Fq / 4x64 Fr Montgomery, 32-bit IMAD limbs)", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "note": "CPU port of the reference's MIDNIGHT_DEVICE=cpu path (Pippenger, OpenMP): BLST/midnight-curves are absent from "
+                "this image (SURVEY.md 8c), oracle/oracle.c stands in; points/s is size-normalised, the sample is in cpu_baseline",
         "cpu_baseline": {"value": r["msm_pts_per_s"], "unit": "points/s", "cores": r["cores"], "kind": "port", "sample": sample},
         "e2e": {"value": r["msm_pts_per_s"], "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "ntt": {"metric": f"fr_ntt_elems_per_s", "value": r["ntt_elems_per_s"], "unit": "elements/s", "log_n": r["ntt_log_n"]},
@@ -191,6 +211,7 @@ def multi_gpu_legs(args, torch, dist, np, M, L, D, lib, rank, world, local_rank,
     nd, loc = 1 << log_d, (1 << log_d) // world
     ctx = M.GpuNttContext(log_d, device_id=local_rank)
     variants = {}
+    oracle_ok = None
     for name, fused in (("fused_p2p", True), ("nccl_all_to_all", False)):
         dn = D.DistributedNtt(log_d, fused=fused)
         ok = True
@@ -198,6 +219,15 @@ def multi_gpu_legs(args, torch, dist, np, M, L, D, lib, rank, world, local_rank,
             x = canonical_fr(torch, nd, 0x26)                     # same vector on every rank
             work = D.column_block_of(x, log_d, rank, world).contiguous()
             rows = dn.forward(work, direction)
+            if direction == 0 and fused and rank == 0 and not args.no_cpu_baseline and log_d <= 26:
+                # independent check (not our own single-GPU transform): rank 0's row block of the distributed result against
+                # the CPU oracle's NTT of the same vector, bit-reversed (kNR order), every byte
+                from oracle import cref as O
+                nat = O.ntt(x.cpu().numpy().view(np.uint64).reshape(-1, 4))
+                nr = O.bit_reverse(nat)
+                del nat
+                oracle_ok = bool((rows.reshape(-1, 4).cpu().numpy().view(np.uint64) == nr[rank * loc:(rank + 1) * loc]).all())
+                del nr
             ctx.ntt_on_device(x.data_ptr(), direction, size=nd, ordering=M.ntt.kNR)
             ok = ok and bool(torch.equal(rows.reshape(-1, 4), x[rank * loc:(rank + 1) * loc]))
             del x, rows
@@ -237,7 +267,9 @@ def multi_gpu_legs(args, torch, dist, np, M, L, D, lib, rank, world, local_rank,
                                             "phases_ms": {"columns": ph_n[0], "all_to_all+transpose": ph_n[1], "rows": ph_n[2]}},
                 "exchange_bytes_per_gpu": loc * 32 * (world - 1) // world,
                 "result_check": "ok (every rank's row block == its single-GPU kNR transform, forward and inverse, both variants)"
-                if ok_f and ok_n else f"MISMATCH (fused ok={ok_f}, nccl ok={ok_n})"}
+                if ok_f and ok_n else f"MISMATCH (fused ok={ok_f}, nccl ok={ok_n})",
+                "oracle_check": None if oracle_ok is None else
+                ("ok (rank 0's row block == oracle.ntt of the whole vector, bit-reversed, bytes)" if oracle_ok else "MISMATCH")}
 
     # ---- (3)
     nb, nk = 8, 1 << 22
@@ -285,6 +317,108 @@ def multi_gpu_legs(args, torch, dist, np, M, L, D, lib, rank, world, local_rank,
                    "ms_per_step": cms, "batch": nb, "log_n": 22, "n_gpus": world, "scaling": "strong",
                    "sharding": "commits dealt round-robin, bases replicated, results all_gather'ed", "result_check": check}
     return shard_check, ntt_dist, commits
+
+
+def reference_gpu_leg(args, torch, np, L, lib, timed, sc, sc_host, bases, n, ours_ntt_ms, ours_vmul_ms, ours_msm):
+    """R-GPU comparator (SURVEY.md 2.2 / BASELINE.md 2): the reference's own kernels, compiled for sm_100 from where the
+    sources lie (oracle/Makefile -> oracle/_ref/), timed on THIS GPU in THIS run through the reference's flat extern "C"
+    API (ntt_kernels.cu:1911-1942, vec_ops.cu:693-838, icicle_curve_api.cu:679-692), beside ours through the same
+    signatures.  Test infrastructure: nothing here is on the product path or inside a timed region of ours."""
+    out = {"what": "the reference's own sm_100 kernels on this GPU, same buffers and flags as ours"}
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    steps = max(2, min(args.steps, 5))
+    f_so, m_so = os.path.join(ref_dir, "libref_field.so"), os.path.join(ref_dir, "libref_msm.so")
+    if os.path.exists(f_so):
+        ref = C.CDLL(f_so)
+        from oracle import pyref as Pr
+        root = np.array(Pr.to_limbs(Pr.fr_to_mont(Pr.fr_omega(24)), 4), dtype=np.uint64)   # what its init assumes (:1614-1644)
+        if ref.bls12_381_ntt_init_domain_cuda(L.ptr(root), C.byref(L.NTTInitDomainConfig())) == 0:
+            nn = min(n, 1 << 24)
+            x, y = sc[:nn].clone(), torch.empty_like(sc[:nn])
+            cfg = lib.b381_default_ntt_config()
+            cfg.are_inputs_on_device = cfg.are_outputs_on_device = True
+
+            def ref_ntt():
+                L.check(ref.bls12_381_ntt_cuda(L.ptr(x), nn, 0, C.byref(cfg), L.ptr(y)), "reference ntt")
+
+            def our_ntt():
+                L.check(lib.bls12_381_ntt_cuda(L.ptr(x), nn, 0, C.byref(cfg), L.ptr(y)), "our ntt, same signature")
+            res = {}
+            for name, fn in (("reference", ref_ntt), ("ours", our_ntt)):
+                fn()
+                fn()
+                ms, _, _ = timed(fn, steps)
+                res[name] = ms / steps
+                res[name + "_sha"] = __import__("hashlib").sha256(y.cpu().numpy().tobytes()).hexdigest()[:16]
+            out["ntt"] = {"log_n": nn.bit_length() - 1, "entry": "bls12_381_ntt_cuda, device in / device out (out != in), kNN",
+                          "reference_ms": res["reference"], "ours_ms": res["ours"], "ours_in_place_ms": ours_ntt_ms,
+                          "speedup": res["reference"] / res["ours"], "same_bytes": res["reference_sha"] == res["ours_sha"]}
+            ref.bls12_381_ntt_release_domain_cuda()
+            del x, y
+        vn = min(n, 1 << 22)
+        a, b, o = sc[:vn], sc[vn:2 * vn] if n >= 2 * vn else sc[:vn], torch.empty_like(sc[:vn])
+        vcfg = lib.b381_default_vecops_config()
+        vcfg.is_a_on_device = vcfg.is_b_on_device = vcfg.is_result_on_device = True
+        res = {}
+        for name, fn in (("reference", ref.bls12_381_vector_mul), ("ours", lib.bls12_381_vector_mul)):
+            def vstep(fn=fn):
+                L.check(fn(L.ptr(a), L.ptr(b), C.c_size_t(vn), C.byref(vcfg), L.ptr(o)), "vector_mul")
+            vstep()
+            vstep()
+            ms, _, _ = timed(vstep, steps * 4)
+            res[name] = ms / (steps * 4)
+            res[name + "_sha"] = __import__("hashlib").sha256(o.cpu().numpy().tobytes()).hexdigest()[:16]
+        out["vector_mul"] = {"log_n": vn.bit_length() - 1, "entry": "bls12_381_vector_mul, device operands",
+                             "reference_ms": res["reference"], "ours_ms": res["ours"], "speedup": res["reference"] / res["ours"],
+                             "same_bytes": res["reference_sha"] == res["ours_sha"], "ours_2^24_ms": ours_vmul_ms}
+        torch.cuda.empty_cache()
+    else:
+        out["ntt"] = out["vector_mul"] = "oracle/_ref/libref_field.so not built (needs /root/reference at build time)"
+    if os.path.exists(m_so):
+        ref = C.CDLL(m_so)
+        from oracle import pyref as Pr
+        # the reference's flat API takes INTEGER-form scalars and Montgomery bases (icicle_curve_api.cu:672-676)
+        rows = []
+        for log_m in (16, 20, 22, 24):
+            m = 1 << log_m
+            if m > n:
+                break
+            sci = torch.empty((m, 4), dtype=torch.int64, device="cuda")
+            vcfg = lib.b381_default_vecops_config()
+            vcfg.is_a_on_device = vcfg.is_result_on_device = True
+            L.check(lib.b381_montgomery_convert(L.ptr(sc), C.c_uint64(m), 0, C.byref(vcfg), L.ptr(sci)), "from_mont")
+            cfg = lib.b381_default_msm_config()
+            cfg.are_scalars_on_device = cfg.are_points_on_device = True
+            cfg.are_scalars_montgomery_form, cfg.are_points_montgomery_form = False, True
+            r_ref, r_our = np.zeros(18, dtype=np.uint64), np.zeros(18, dtype=np.uint64)
+            t0 = time.perf_counter()
+            rc = ref.bls12_381_g1_msm_cuda(L.ptr(sci), L.ptr(bases), m, C.byref(cfg), L.ptr(r_ref))
+            torch.cuda.synchronize()
+            first_s = time.perf_counter() - t0
+            if rc != 0:
+                rows.append({"log_n": log_m, "reference": f"failed with code {rc}"})
+                break
+            k = 1 if first_s > 2.0 else 3
+            ms_ref, _, _ = timed(lambda: ref.bls12_381_g1_msm_cuda(L.ptr(sci), L.ptr(bases), m, C.byref(cfg), L.ptr(r_ref)), k)
+            L.check(lib.bls12_381_g1_msm_cuda(L.ptr(sci), L.ptr(bases), m, C.byref(cfg), L.ptr(r_our)), "our msm, same signature")
+            ms_our, _, _ = timed(lambda: lib.bls12_381_g1_msm_cuda(L.ptr(sci), L.ptr(bases), m, C.byref(cfg), L.ptr(r_our)), 3)
+
+            def affine(j):                       # Jacobian Montgomery (X, Y, Z) -> affine integers
+                X, Y, Z = (Pr.fq_from_mont(Pr.from_limbs(j[6 * i:6 * i + 6])) for i in range(3))
+                if Z == 0:
+                    return None
+                zi = pow(Z, -1, Pr.P_MOD)
+                return (X * zi * zi % Pr.P_MOD, Y * zi * zi * zi % Pr.P_MOD)
+            rows.append({"log_n": log_m, "reference_ms": ms_ref / k, "ours_ms": ms_our / 3, "speedup": (ms_ref / k) / (ms_our / 3),
+                         "same_point": affine(r_ref) == affine(r_our)})
+            del sci
+            if first_s > 20.0:
+                break
+        out["g1_msm"] = {"entry": "bls12_381_g1_msm_cuda, device integer-form scalars, resident Montgomery bases, host result",
+                         "sizes": rows, "ours_headline_ms": ours_msm}
+    else:
+        out["g1_msm"] = "oracle/_ref/libref_msm.so not built (needs /root/reference at build time; ~6 min of cicc)"
+    return out
 
 
 def main():
@@ -346,35 +480,40 @@ def main():
         if rank == 0:
             result["r"] = msm.combine(parts)
 
-    # e2e: host (pinned) scalars -> device inside the timed region.  Two staging buffers and a copy stream:
-    # the H2D of step i+1 runs under the compute of step i, as the reference's async batch-commit API
-    # (core/msm.rs:1314-1418, docs/gpu-integration batch_commit) is meant to be driven.
-    stages = [torch.empty_like(sc), torch.empty_like(sc)]
-    copy_stream = torch.cuda.Stream()
-    ready = [torch.cuda.Event(), torch.cuda.Event()]
-    consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    e2e_state = {"i": 0, "primed": False}
-
-    def prefetch(slot):
-        with torch.cuda.stream(copy_stream):
-            copy_stream.wait_event(consumed[slot])
-            stages[slot].copy_(sc_host, non_blocking=True)
-            ready[slot].record(copy_stream)
+    # e2e: the plugin call itself.  Host (pinned) scalars, resident bases, are_scalars_on_device = false: the library stages
+    # the scalars in (H2D on the caller's stream), runs the MSM and writes the result to host memory -- exactly what ICICLE's
+    # dispatcher does through msm_cuda_impl's replacement (icicle_curve_api.cu:243-407).  Synchronous, one call per step.
+    host_cfg = lib.b381_default_msm_config()
+    host_cfg.are_scalars_on_device, host_cfg.are_points_on_device = False, True
+    host_cfg.are_scalars_montgomery_form = host_cfg.are_points_montgomery_form = True
+    e2e_part = torch.empty(24, dtype=torch.int64, device="cuda")          # one XYZZ partial (N > 1 only)
+    e2e_res = np.zeros(18, dtype=np.uint64)
 
     def step_e2e():
-        i = e2e_state["i"]
-        slot = i & 1
-        if not e2e_state["primed"]:
-            prefetch(slot)
-            e2e_state["primed"] = True
-        prefetch(slot ^ 1)                                  # next step's scalars, overlapped
-        torch.cuda.current_stream().wait_event(ready[slot])
-        part = msm.partial(stages[slot], bases, n_loc, scalars_mont=True)
-        consumed[slot].record(torch.cuda.current_stream())
-        parts = D.gather_partials(part)
-        if rank == 0:
-            result["e2e"] = msm.combine(parts)               # D2H of the 144-byte result
-        e2e_state["i"] = i + 1
+        if world == 1:
+            L.check(lib.b381_g1_msm(L.ptr(sc_host), L.ptr(bases), n_loc, C.byref(host_cfg), L.ptr(e2e_res)), "plugin msm")
+            result["e2e"] = e2e_res
+        else:
+            L.check(lib.b381_g1_msm_partial(L.ptr(sc_host), L.ptr(bases), n_loc, C.byref(host_cfg), L.ptr(e2e_part)), "plugin partial")
+            parts = D.gather_partials(e2e_part)
+            if rank == 0:
+                result["e2e"] = msm.combine(parts)               # D2H of the 144-byte result
+
+    # e2e_pipelined (N = 1): the host API's async calls, each on its own stream with its own H2D
+    # (core/msm.rs:715-798, :1314-1418): two commits in flight, so the copy of one rides under the other's kernels.
+    def run_pipelined(k):
+        ctx = M.GpuMsmContext(device_id=local_rank)
+        from midnight_bls12_381_cuda_b200.stream import DeviceVec
+        dev_bases = M.msm.PrecomputedBases(DeviceVec.borrow(bases.data_ptr(), n_loc, 96), n_loc)
+        sc_np = sc_host.numpy().view(np.uint64)
+        pending, out = [], None
+        for _ in range(k):
+            pending.append(ctx.msm_with_device_bases_async(sc_np, dev_bases))
+            if len(pending) == 2:
+                out = pending.pop(0).wait()
+        while pending:
+            out = pending.pop(0).wait()
+        return out
 
     def barrier():
         if world > 1:
@@ -415,52 +554,94 @@ def main():
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
+    ms_pipe, pipe_xy = None, None
+    if world == 1:
+        run_pipelined(2)
+        box = {}
+        ms_pipe, _, _ = timed(lambda: box.__setitem__("xy", run_pipelined(args.steps)), 1)
+        pipe_xy = box["xy"]
 
-    # ---- NTT 2^24: every rank transforms its own resident vector (replicas; four-step is exercised by tests/dist)
+    # ---- NTT 2^24: every rank transforms its own resident vector (replicas; the four-step transform is in multi_gpu_legs)
     ntt_ctx = M.GpuNttContext(args.log_n, device_id=local_rank)
     vec = sc.clone()                                   # canonical Montgomery words
     vec_host = sc_host
     ntt_out_host = torch.empty_like(sc_host).pin_memory() if n_loc == n else None
+    ntt_size = n_loc if n_loc & (n_loc - 1) == 0 else n
 
     def ntt_step():
-        ntt_ctx.ntt_on_device(vec.data_ptr(), 0, size=n_loc if n_loc & (n_loc - 1) == 0 else n)
+        ntt_ctx.ntt_on_device(vec.data_ptr(), 0, size=ntt_size)
 
     ntt_ok = n_loc & (n_loc - 1) == 0
     ntt = None
     if ntt_ok:
+        # one-off check outside the timed region: every byte of the forward kNN transform against the CPU oracle
+        ntt_check = "skipped"
+        if rank == 0 and not args.no_cpu_baseline and ntt_size <= (1 << 26):
+            from oracle import cref as O
+            ntt_step()
+            got = vec.cpu().numpy().view(np.uint64).reshape(-1, 4)
+            exp = O.ntt(sc_host.numpy().view(np.uint64).reshape(-1, 4)[:ntt_size])
+            ntt_check = "ok" if (got[:ntt_size] == exp).all() else "MISMATCH"
+            del got, exp
+            vec.copy_(sc)
         for _ in range(args.warmup):
             ntt_step()
         ntt_ms, _, _ = timed(ntt_step, args.steps)
         ntt_ms /= args.steps
         ntt_e2e = None
         if ntt_out_host is not None:
+            # the plugin call with HOST buffers: b381_ntt stages in, transforms, copies out (icicle_field_api.cu:97-131)
+            ncfg = lib.b381_default_ntt_config()
+            ncfg.are_inputs_on_device = ncfg.are_outputs_on_device = False
+
             def ntt_e2e_step():
-                vec.copy_(vec_host, non_blocking=True)
-                ntt_step()
-                ntt_out_host.copy_(vec, non_blocking=True)
+                L.check(lib.b381_ntt(L.ptr(vec_host), ntt_size, 0, C.byref(ncfg), L.ptr(ntt_out_host)), "plugin ntt")
             ntt_e2e_step()
-            ms, _, _ = timed(ntt_e2e_step, max(1, args.steps // 2))
-            ntt_e2e = ms / max(1, args.steps // 2)
+            k = max(1, args.steps // 2)
+            ms, _, _ = timed(ntt_e2e_step, k)
+            ntt_e2e = ms / k
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except OSError:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        passes = 1 if args.log_n <= 11 else (2 if args.log_n <= 20 else 3)
+        ninfo = (C.c_int * 4)()
+        passes = lib.b381_ntt_last_info(ninfo, 4) and ninfo[0]
         alg_bytes = 128.0 * n_loc          # 2^13..2^24 -> 128 B/element (two ideal passes)
         ntt = {"metric": f"fr_ntt_2^{n_loc.bit_length() - 1}_elements_per_s", "value": n_loc * world / (ntt_ms * 1e-3),
                "unit": "elements/s", "ms_per_step": ntt_ms, "scaling": "weak (one resident transform per GPU)" if world > 1 else "single",
-               "e2e": None if ntt_e2e is None else {"value": n_loc / (ntt_e2e * 1e-3), "unit": "elements/s",
-                                                     "h2d_bytes_per_step": n_loc * 32, "d2h_bytes_per_step": n_loc * 32},
+               "e2e": None if ntt_e2e is None else {"value": n_loc / (ntt_e2e * 1e-3), "unit": "elements/s", "ms_per_step": ntt_e2e,
+                                                     "h2d_bytes_per_step": n_loc * 32, "d2h_bytes_per_step": n_loc * 32,
+                                                     "note": "b381_ntt with pinned HOST input and output (are_inputs_on_device = "
+                                                             "are_outputs_on_device = false); PCIe-bound: 2 x 0.5 GiB per transform"},
                "roofline": {"bound": "hbm", "achieved": alg_bytes / (ntt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak,
-                            # dram__bytes_read+write of the three k_ntt_pass launches of one 2^24 transform, ncu --set full
-                            # (profiles/r01d_ntt_pass_key_metrics.txt: 1.57 + 1.02 + 1.06 GB), per launch average
-                            "traffic": (3.65e9 / 3) if args.log_n == 24 and world == 1 else None,
-                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
-                            "kernel": f"k_ntt_pass x{passes}", "note": "compute (IMAD) bound: see imad_frac"},
-               "gpu_launches": passes}
+                            "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                            "kernel": f"k_ntt x{passes}", "note": "compute (IMAD) bound: see imad_frac / fr_mul_floor_frac"},
+               "result_check": ntt_check, "gpu_launches": passes}
+
+    # ---- vecops 2^24 (96 B/element a o b, 64 B scalar o vec), resident operands, HBM roofline
+    vec_ops = None
+    if world == 1 and ntt is not None:
+        va, vb, vo = sc, vec, torch.empty_like(sc)
+        vcfg = lib.b381_default_vecops_config()
+        vcfg.is_a_on_device = vcfg.is_b_on_device = vcfg.is_result_on_device = True
+        one_elem = sc[:1].clone()
+        vec_ops = {}
+        for name, fn, a0, bytes_per in (("vector_mul", lib.b381_vector_mul, va, 96.0), ("vector_add", lib.b381_vector_add, va, 96.0),
+                                        ("scalar_mul_vec", lib.b381_scalar_mul_vec, one_elem, 64.0)):
+            def vstep(fn=fn, a0=a0):
+                L.check(fn(L.ptr(a0), L.ptr(vb), C.c_uint64(n_loc), C.byref(vcfg), L.ptr(vo)), name)
+            for _ in range(3):
+                vstep()
+            ms, _, _ = timed(vstep, args.steps)
+            ms /= args.steps
+            gbs = bytes_per * n_loc / (ms * 1e-3) / 1e9
+            vec_ops[name] = {"ms": ms, "elements_per_s": n_loc / (ms * 1e-3),
+                             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                                          "bytes_per_element": bytes_per, "kernel": "k_vecop"}}
+        del vo
 
     # ---- roofline denominators measured on this box, now (rank 0)
     # ---- G2 MSM 2^20 (BASELINE.json config 4), single GPU only: bases (1+i) G2 resident, first 2^20 scalars
@@ -537,6 +718,9 @@ def main():
             # n/2 * log2(n) butterflies, one Fr Montgomery product (2*8^2+8 = 136 multiply-adds) each
             ln = n_loc.bit_length() - 1
             ntt["roofline"]["imad_frac"] = (0.5 * n_loc * ln * 136) / (ntt["ms_per_step"] * 1e-3) / imad_peak
+            # floor = n/2 * log2(n) Fr products at the fr_mul rate measured by the probe in this run
+            ntt["roofline"]["fr_mul_floor_ms"] = 0.5 * n_loc * ln / fr_rate * 1e3
+            ntt["roofline"]["fr_mul_floor_frac"] = ntt["roofline"]["fr_mul_floor_ms"] / ntt["ms_per_step"]
         # one-off correctness check outside the timed region (oracle as checker): sum s_i (beg+1+i) G
         check = "skipped"
         if world == 1 and not args.no_cpu_baseline:
@@ -548,7 +732,8 @@ def main():
                 kk[:, 0] = np.arange(1, n + 1, dtype=np.uint64)
                 dl = Pr.from_limbs(O.fr_dot(s_np, kk, s_mont=True))
                 exp = Pr.g1_result_std_bytes(Pr.g1_mul(dl, Pr.G1_GEN))
-                check = "ok" if result["r"].tobytes() == exp and result["e2e"].tobytes() == exp else "MISMATCH"
+                pipe_ok = pipe_xy is None or (pipe_xy[0].to_bytes(48, "little") + pipe_xy[1].to_bytes(48, "little")) == exp[:96]
+                check = "ok" if result["r"].tobytes() == exp and result["e2e"].tobytes() == exp and pipe_ok else "MISMATCH"
                 if g2 is not None:
                     kk2 = np.zeros((1 << 20, 4), dtype=np.uint64)
                     kk2[:, 0] = np.arange(1, (1 << 20) + 1, dtype=np.uint64)
@@ -559,29 +744,42 @@ def main():
                 check = f"error: {e}"
         cpu = None
         if not args.no_cpu_baseline and world == 1:
-            cl = args.cpu_log_n or 18
-            r = cpu_leg(cl, 2, 0)
+            cl = args.cpu_log_n or 20
+            r = cpu_leg(cl, 3, 1)
             cpu = {"value": r["msm_pts_per_s"], "unit": "points/s", "cores": r["cores"], "kind": "port",
-                   "sample": f"G1 MSM 2^{cl} of the 2^{args.log_n} workload x2 (oracle/oracle.c, OpenMP); NTT 2^{r['ntt_log_n']}: "
+                   "sample": f"G1 MSM 2^{cl} of the 2^{args.log_n} workload x3 after one warm-up (oracle/oracle.c, OpenMP); NTT 2^{r['ntt_log_n']}: "
                              f"{r['ntt_elems_per_s']:.3e} elements/s"}
+        ref_gpu = None
+        if world == 1 and not args.no_reference_gpu:
+            try:
+                ref_gpu = reference_gpu_leg(args, torch, np, L, lib, timed, sc, sc_host, bases, n,
+                                            ntt["ms_per_step"] if ntt else None,
+                                            vec_ops["vector_mul"]["ms"] if vec_ops else None, ms_step)
+            except Exception as e:  # noqa: BLE001
+                ref_gpu = {"error": repr(e)}
         out = {
             "metric": f"g1_msm_2^{args.log_n}_points_per_s", "value": n / (ms_step * 1e-3), "unit": "points/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "u64 (6x64 Fq / 4x64 Fr Montgomery, 32-bit IMAD limbs)",
             "data": "synthetic",
-            "config": {"workload": f"G1 MSM n=2^{args.log_n}, bases (1+i)G resident in HBM, uniform Montgomery scalars; "
-                                   f"window c={c_win} signed digits, {levels} affine pre-reduction levels; + Fr NTT 2^{args.log_n} (kNN, in place)",
-                       "sharding": f"{world} contiguous point ranges, one XYZZ partial per GPU, NCCL all_gather" if world > 1 else "single GPU",
-                       "l2": "inputs (0.5 GiB scalars + 1.5 GiB bases) exceed the 126 MB L2; no flush needed"},
+            "config": workload_config(args, world),
+            "msm_shape": {"window_c": c_win, "windows": W, "affine_levels": levels},
             "e2e": {"value": n / (ms_e2e / args.steps * 1e-3), "unit": "points/s", "h2d_bytes_per_step": n_loc * 32,
                     "d2h_bytes_per_step": 144, "ms_per_step": ms_e2e / args.steps,
-                    "note": "pinned-host scalars; H2D of step i+1 overlaps compute of step i (copy stream, 2 staging buffers)"},
+                    "note": "the plugin call: b381_g1_msm" + ("" if world == 1 else "_partial + all_gather + combine") +
+                            " with pinned HOST scalars (are_scalars_on_device = false), resident bases, synchronous, "
+                            "result to host"},
+            "e2e_pipelined": None if ms_pipe is None else {
+                "value": n / (ms_pipe / args.steps * 1e-3), "unit": "points/s", "ms_per_step": ms_pipe / args.steps,
+                "h2d_bytes_per_step": n_loc * 32, "d2h_bytes_per_step": 144,
+                "note": "GpuMsmContext.msm_with_device_bases_async (own stream per call, host scalars staged by the plugin call), "
+                        "two commits in flight"},
             "gpu_launches": (own_launches + 1) * args.steps,
             "gpu_launches_note": "own kernels per MSM step as counted by the library (b381_msm_last_info): digits, offsets, "
                                  "4 per affine level, task_count/build_tasks/task_keys, accumulate, finalize, segment, tree levels, "
                                  "combine, + encode (CUB radix sort / scan kernels not counted)",
             "phases_ms": dict(zip(names, [round(x, 4) for x in ph[:8]])),
-            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "ntt": ntt,
+            "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "ntt": ntt, "vecops": vec_ops, "reference_gpu": ref_gpu,
             "g2": None if g2 is None else {k: v for k, v in g2.items() if k != "result"},
             "probes": {"imad_wide_mad_per_s": imad_peak, "fq_mul_per_s": fq_rate, "fr_mul_per_s": fr_rate},
             "result_check": check if world == 1 else shard_check,

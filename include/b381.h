@@ -67,7 +67,8 @@ typedef struct {
   void* stream;                    /* cudaStream_t */
   int precompute_factor;
   int c;                           /* window bits, 0 = auto */
-  int bitsize;                     /* scalar bits, 0 = 255 */
+  int bitsize;                     /* scalar bits; 0 = 255, the bit length of r (the reference reads 0 as 256 = 4 limbs,
+                                      msm_kernels.cu:651: same digits for canonical scalars, one more empty window) */
   int batch_size;
   bool are_points_shared_in_batch;
   bool are_scalars_on_device;
@@ -136,7 +137,7 @@ int b381_g2_msm_precompute_bases(const b381_g2_affine* input_bases, int bases_si
  * reference's CUDA tests pass, tests/test_ntt_security.cu:1034-1043); its order 2^k (k<=32) is
  * discovered, not assumed. */
 int b381_ntt_init_domain(const b381_fr* primitive_root, const b381_ntt_init_domain_config* config);
-int b381_ntt_release_domain(void);
+int b381_ntt_release_domain(void);   /* releases the CURRENT device's domain; domains are per device */
 /* replaces ntt_cuda_impl (ntt_kernels.cu:968-1133) and coset_ntt_cuda_impl (:1155-1306);
  * honours ordering, coset_gen, batch_size, columns_batch and stream. size = one NTT's length. */
 int b381_ntt(const b381_fr* input, int size, int dir, const b381_ntt_config* config, b381_fr* output);
@@ -282,6 +283,8 @@ int b381_msm_last_info(int* out, int cap);
 /* duration of the two dominant kernels of the most recent G1 MSM on this thread (level-0 forward and backward pass
  * of the affine pre-reduction), CUDA events on the launching stream, B381_MSM_TIMING=1; returns 1 if available. */
 int b381_msm_last_level0_ms(float* fwd_ms, float* bwd_ms);
+/* shape of the most recent NTT on this thread: [kernel launches (passes), log2 size, batch, 0]; returns count written. */
+int b381_ntt_last_info(int* out, int cap);
 const char* b381_version(void);
 
 #ifdef __cplusplus

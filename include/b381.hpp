@@ -98,7 +98,11 @@ class DeviceVec {
 
 class PrecomputedBases {
  public:
-  PrecomputedBases(DeviceVec<G1Affine>&& buf, size_t size, int factor = 1) : buf_(std::move(buf)), size_(size), factor_(factor) {}
+  // Precomputed buffers hold point i's multiples interleaved at [i*factor + k]; `window` is the cfg.c the table was
+  // built with (0 = the backend's fixed default for precomputed bases) and is reused by every MSM over it.
+  PrecomputedBases(DeviceVec<G1Affine>&& buf, size_t size, int factor = 1, int window = 0)
+      : buf_(std::move(buf)), size_(size), factor_(factor), window_(window) {}
+  int window() const { return window_; }
   bool is_precomputed() const { return factor_ > 1; }
   int factor() const { return factor_; }
   size_t original_size() const { return size_; }
@@ -110,6 +114,7 @@ class PrecomputedBases {
   DeviceVec<G1Affine> buf_;
   size_t size_;
   int factor_;
+  int window_ = 0;
 };
 
 class MsmHandle {
@@ -150,7 +155,7 @@ class GpuMsmContext {
     cfg.precompute_factor = factor;
     cfg.are_results_on_device = true;
     check(b381_g1_msm_precompute_bases(bases.device_ptr(), (int)bases.original_size(), &cfg, out.data()), "precompute_bases");
-    return PrecomputedBases(std::move(out), bases.original_size(), factor);
+    return PrecomputedBases(std::move(out), bases.original_size(), factor, window_);
   }
   // core/msm.rs:519-592
   G1Projective msm(const std::vector<Scalar>& scalars, const std::vector<G1Affine>& points) const {
@@ -165,12 +170,13 @@ class GpuMsmContext {
     if (scalars.size() > bases.original_size()) throw Error(B381_INVALID_ARGUMENT, "more scalars than bases");
     G1Projective r{};
     b381_msm_config cfg = config(true);
-    cfg.precompute_factor = bases.factor();
+    apply(cfg, bases);
     check(b381_g1_msm(scalars.data(), bases.device_ptr(), (int)scalars.size(), &cfg, &r), "msm_with_device_bases");
     return r;
   }
   // core/msm.rs:715-798
   MsmHandle msm_with_device_bases_async(const std::vector<Scalar>& scalars, const PrecomputedBases& bases) const {
+    if (scalars.size() > bases.original_size()) throw Error(B381_INVALID_ARGUMENT, "more scalars than bases");
     ManagedStream st = ManagedStream::create();
     DeviceVec<Scalar> staged(scalars.size());
     check(b381_copy_to_device_async(staged.data(), scalars.data(), scalars.size() * sizeof(Scalar), st.handle()), "h2d");
@@ -179,7 +185,7 @@ class GpuMsmContext {
     cfg.are_scalars_on_device = true;
     cfg.is_async = true;
     cfg.stream = h.stream();
-    cfg.precompute_factor = bases.factor();
+    apply(cfg, bases);
     check(b381_g1_msm(h.scalars(), bases.device_ptr(), (int)scalars.size(), &cfg, h.slot()), "msm async");
     return h;
   }
@@ -187,6 +193,7 @@ class GpuMsmContext {
   std::vector<G1Projective> msm_batch_with_device_bases(const std::vector<std::vector<Scalar>>& batch, const PrecomputedBases& bases) const {
     if (batch.empty()) return {};
     const size_t n = batch[0].size();
+    if (n > bases.original_size()) throw Error(B381_INVALID_ARGUMENT, "more scalars than bases");
     std::vector<Scalar> flat;
     flat.reserve(n * batch.size());
     for (auto& v : batch) {
@@ -197,7 +204,7 @@ class GpuMsmContext {
     b381_msm_config cfg = config(true);
     cfg.batch_size = (int)batch.size();
     cfg.are_points_shared_in_batch = true;
-    cfg.precompute_factor = bases.factor();
+    apply(cfg, bases);
     check(b381_g1_msm(flat.data(), bases.device_ptr(), (int)n, &cfg, out.data()), "msm batch");
     return out;
   }
@@ -223,6 +230,11 @@ class GpuMsmContext {
     c.are_points_montgomery_form = true;
     c.are_points_on_device = points_on_device;
     return c;
+  }
+  // precomputed tables fix the factor AND the window they were built with
+  static void apply(b381_msm_config& c, const PrecomputedBases& bases) {
+    c.precompute_factor = bases.factor();
+    if (bases.is_precomputed()) c.c = bases.window();
   }
   int window_;
 };

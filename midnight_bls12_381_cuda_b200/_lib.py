@@ -85,7 +85,7 @@ EXPORTS = [
     "b381_stream_create", "b381_stream_destroy", "b381_stream_synchronize", "b381_device_synchronize",
     "b381_ntt_dist_columns", "b381_ntt_dist_columns_p2p", "b381_ipc_alloc", "b381_ipc_open", "b381_ipc_close", "b381_g1_msm_partial", "b381_g2_msm_partial", "b381_g1_msm_combine", "b381_g2_msm_combine",
     "b381_g1_point_series", "b381_g2_point_series",
-    "b381_bench_imad_peak", "b381_bench_field_mul", "b381_msm_last_timings", "b381_msm_last_info", "b381_msm_last_level0_ms", "b381_version",
+    "b381_bench_imad_peak", "b381_bench_field_mul", "b381_msm_last_timings", "b381_msm_last_info", "b381_msm_last_level0_ms", "b381_ntt_last_info", "b381_version",
 ]
 
 

@@ -39,16 +39,15 @@ inline int map_cuda_error(cudaError_t e) {
 
 // Keep freed scratch cached in the default pool instead of returning it to the driver.
 inline void configure_pool_once() {
-  static bool done = false;
-  if (done) return;
+  static bool done[64] = {};                 // per device: a single process may drive several GPUs
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
-  done = true;
+  done[dev] = true;
 }
 
 // RAII bag of stream-ordered allocations; everything is released (asynchronously, in stream

@@ -137,6 +137,14 @@ template <class F> B381_DI affine_t<F> xyzz_to_affine(const xyzz_t<F>& p) {
   return affine_t<F>{mul(p.x, iz2), mul(p.y, iz3)};
 }
 
+// curve constant b (Montgomery): 4 on G1, 4(1 + u) on G2; y^2 = x^3 + b  (point.cuh:339-387)
+template <class F> B381_DI F curve_b();
+template <> B381_DI fq_t curve_b<fq_t>() { fq_t two = dbl(one<fq_t>()); return dbl(two); }
+template <> B381_DI fq2_t curve_b<fq2_t>() { fq_t f = curve_b<fq_t>(); return fq2_t{f, f}; }
+template <class F> B381_DI bool on_curve(const affine_t<F>& p) {
+  return is_inf(p) || eq(sqr(p.y), add(mul(sqr(p.x), p.x), curve_b<F>()));
+}
+
 // Jacobian (reference wire format) -> XYZZ: ZZ = Z^2, ZZZ = Z^3
 template <class F> B381_DI xyzz_t<F> jac_to_xyzz(const jacobian_t<F>& p) {
   if (is_zero(p.z)) return xyzz_identity<F>();

@@ -48,8 +48,10 @@ class B200DeviceAPI : public DeviceAPI {
                  eIcicleError::SYNCHRONIZATION_FAILED);
   }
   eIcicleError create_stream(icicleStreamHandle* s) const override {
+    // plain cudaStreamCreate like the reference (cuda_device_api.cu:127-133): ICICLE's callers may mix such a stream
+    // with default-stream work and rely on the legacy implicit ordering between the two
     cudaStream_t st;
-    cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+    cudaError_t e = cudaStreamCreate(&st);
     if (e == cudaSuccess) *s = st;
     return ok_or(e, eIcicleError::STREAM_CREATION_FAILED);
   }
@@ -58,7 +60,7 @@ class B200DeviceAPI : public DeviceAPI {
   }
   eIcicleError get_device_properties(DeviceProperties& p) const override {
     p.using_host_memory = false;
-    p.num_memory_regions = 0;
+    p.num_memory_regions = 1;             // cuda_device_api.cu:141-147
     p.supports_pinned_memory = true;
     return eIcicleError::SUCCESS;
   }

@@ -26,7 +26,6 @@
 //                                                           [ref: :529-596 + icicle_curve_api.cu:134-229]
 #pragma once
 #include "curve.cuh"
-#include "fq_lazy.cuh"
 #include "msm_batch.cuh"
 
 namespace b381 {
@@ -39,11 +38,14 @@ struct msm_shape {
   uint32_t Wf;       // bucket sets after folding with precomputed bases: ceil(W / precompute_factor)
   uint32_t Bs;       // bucket slots per set = B + 1: slot B of every set is its trash bucket (zero digits)
   uint32_t nbuckets; // Wf*Bs bucket slots, trash slots included
+  uint32_t f;        // precompute_factor (>= 1): point i has f stored multiples, at bases[i*f + k]
 };
 
-// With precompute_factor f the caller supplies f*n bases, block k holding 2^(k*Wf*c) * P_i, and
-// window w = k*Wf + w' is inserted into bucket set w' using base block k -- all windows of one
-// residue class share buckets, so only Wf bucket sets are reduced and combined.
+// With precompute_factor f the caller supplies f*n bases, point i's multiples 2^(k*Wf*c) * P_i (k < f) stored
+// INTERLEAVED at bases[i*f + k] -- upstream ICICLE's layout, which lets an MSM over the first n' < n points use a
+// prefix of the same buffer (core/msm.rs:654-661 passes the full buffer whatever scalars.len() is).  Window
+// w = k*Wf + w' is inserted into bucket set w' using multiple k -- all windows of one residue class share buckets,
+// so only Wf bucket sets are reduced and combined.
 B381_HD msm_shape make_msm_shape(uint32_t n, uint32_t c, uint32_t bits, uint32_t factor) {
   msm_shape sh;
   sh.n = n;
@@ -54,6 +56,7 @@ B381_HD msm_shape make_msm_shape(uint32_t n, uint32_t c, uint32_t bits, uint32_t
   sh.Wf = (sh.W + factor - 1) / factor;
   sh.Bs = sh.B + 1;
   sh.nbuckets = sh.Wf * sh.Bs;
+  sh.f = factor;
   return sh;
 }
 
@@ -106,7 +109,7 @@ B381_DI void msm_digits_body(uint32_t i, const fr_t* scalars, bool scalars_mont,
     uint32_t blk = w / sh.Wf, wf = w - blk * sh.Wf;
     uint32_t key = (local_keys ? 0u : wf * sh.Bs) + (d ? d - 1 : sh.B);
     keys[(size_t)w * sh.n + i] = key;
-    vals[(size_t)w * sh.n + i] = ((blk * sh.n + i) << 1) | sign;
+    vals[(size_t)w * sh.n + i] = ((i * sh.f + blk) << 1) | sign;
   }
   // W*c >= 256 > bit length of any canonical scalar, so the last carry is always 0.
 }
@@ -192,28 +195,6 @@ B381_DI void msm_accumulate_body(uint32_t t, uint32_t ntasks, const uint2* tasks
     xyzz_madd(acc, p);
   }
   partial[t] = acc;
-}
-
-// Experimental G1 variant (B381_ACC_LAZY=1): the same loop on carry-free lazy-reduced limbs
-// (fq_lazy.cuh).  Bit-exact, but on B200 it measured SLOWER than the saturated loop above (167 ms vs
-// 116 ms at 2^24): ptxas turns the mad.wide chains into products + 3-input adds (2.2x the instructions)
-// and the 64-bit-accumulate IMAD.WIDE issues at ~3.1 cycles here, so the heavy pipe saves nothing.
-// Kept selectable as evidence and as the starting point for a SASS-level version; see DESIGN.md.
-B381_DI void msm_accumulate_lazy_body(uint32_t t, uint32_t ntasks, const uint2* tasks, const uint32_t* sorted_vals,
-                                      const affine_t<fq_t>* bases, xyzz_t<fq_t>* partial, const uint32_t* order = nullptr) {
-  if (order) t = order[t];
-  if (t >= ntasks) return;
-  uint2 tk = tasks[t];
-  g1_lazy_acc acc;
-  acc.inf = true;
-  for (uint32_t j = tk.x; j < tk.y; j++) {
-    uint32_t v = sorted_vals[j];
-    affine_t<fq_t> p = bases[v >> 1];
-    if (is_inf(p)) continue;
-    if (v & 1) p.y = neg(p.y);
-    lazy_madd(acc, p.x, p.y);
-  }
-  partial[t] = lazy_to_xyzz(acc);
 }
 
 // ---------------------------------------------------------------- 6 finalize

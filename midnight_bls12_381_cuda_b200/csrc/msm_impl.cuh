@@ -68,21 +68,6 @@ __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* nt
   msm_accumulate_body<F>(t, *ntasks_dev, tasks, sorted_vals, bases, partial, order);
 }
 
-static __global__ void __launch_bounds__(128, 3) k_msm_accumulate_lazy(const uint32_t* ntasks_dev, const uint2* tasks,
-                                                               const uint32_t* sorted_vals, const g1_affine* bases,
-                                                               g1_xyzz* partial, const uint32_t* order) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_accumulate_lazy_body(t, *ntasks_dev, tasks, sorted_vals, bases, partial, order);
-}
-template <class F> static bool launch_lazy(unsigned, cudaStream_t, const uint32_t*, const uint2*, const uint32_t*, const affine_t<F>*, xyzz_t<F>*, const uint32_t*) { return false; }
-template <> inline bool launch_lazy<fq_t>(unsigned g, cudaStream_t st, const uint32_t* nt, const uint2* tasks, const uint32_t* sv,
-                                   const g1_affine* bases, g1_xyzz* partial, const uint32_t* order) {
-  const char* e = getenv("B381_ACC_LAZY");
-  if (!e || e[0] != '1') return false;
-  k_msm_accumulate_lazy<<<g, 128, 0, st>>>(nt, tasks, sv, bases, partial, order);
-  return true;
-}
-
 // ---- affine pre-reduction (msm_batch.cuh): three kernels per level, no barriers ----------------
 static __global__ void k_msm_half_counts(const uint32_t* offsets, uint32_t nbuckets, uint32_t Bs, uint32_t* counts) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,18 +118,39 @@ __global__ void k_points_to_mont(const affine_t<F>* in, affine_t<F>* out, uint32
   out[i] = affine_t<F>{to_mont(p.x), to_mont(p.y)};
 }
 
-// out[k*n + i] = 2^(k*shift_bits) * in[i]  (affine Montgomery), one thread per input point.
+// out[i*factor + k] = 2^(k*shift_bits) * in[i], one thread per input point.  `in` is Montgomery affine (the entry
+// point converted it if needed); `out` is written in the form the caller declared for the input, like upstream
+// ICICLE's precompute_bases does.
 template <class F>
 __global__ void __launch_bounds__(64) k_precompute_bases(const affine_t<F>* in, affine_t<F>* out, uint32_t n,
-                                                         uint32_t factor, uint32_t shift_bits) {
+                                                         uint32_t factor, uint32_t shift_bits, bool out_mont) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   affine_t<F> p = in[i];
-  out[i] = p;
   xyzz_t<F> acc = to_xyzz(p);
-  for (uint32_t k = 1; k < factor; k++) {
-    for (uint32_t b = 0; b < shift_bits; b++) acc = xyzz_dbl(acc);
-    out[(size_t)k * n + i] = xyzz_to_affine(acc);
+  for (uint32_t k = 0; k < factor; k++) {
+    if (k) {
+      for (uint32_t b = 0; b < shift_bits; b++) acc = xyzz_dbl(acc);
+      p = xyzz_to_affine(acc);
+    }
+    out[(size_t)i * factor + k] = out_mont ? p : affine_t<F>{from_mont(p.x), from_mont(p.y)};
+  }
+}
+
+// Which form are these points in?  The reference's Rust layer declares precomputed bases Montgomery when it
+// builds them and NOT Montgomery when it uses them (core/msm.rs:450 vs :641-643), so for precompute_factor > 1
+// the flag cannot be trusted: the first finite point is tested against y^2 = x^3 + b read as Montgomery words.
+// A point satisfies the equation in both readings with probability ~2^-381.  *flag = 1 Montgomery, 0 not, 2 = no
+// finite point among the first `count` (either reading gives the identity).
+template <class F>
+__global__ void k_points_form_probe(const affine_t<F>* pts, uint32_t count, int* flag) {
+  if (blockIdx.x || threadIdx.x) return;
+  *flag = 2;
+  for (uint32_t i = 0; i < count; i++) {
+    affine_t<F> p = pts[i];
+    if (is_inf(p)) continue;
+    *flag = on_curve(p) ? 1 : 0;
+    return;
   }
 }
 
@@ -197,9 +203,13 @@ static uint32_t ceil_log2_u64(uint64_t v) {
 // with W = ceil((bits+1)/c), capped at c = 16: beyond that the per-bucket load (n / 2^(c-1)) gets so
 // small that warp divergence in the accumulate kernel eats the saving (measured on B200: 2^24 points,
 // c = 16 -> 130 ms, c = 20 -> 191 ms; profiles/r01_msm_window_sweep.txt).
+constexpr uint32_t kPrecomputeWindow = 16;   // cfg.c == 0 with precompute_factor > 1
 static uint32_t pick_window(uint32_t n, uint32_t bits, uint32_t factor, bool g1 = true) {
   const char* e = getenv("B381_MSM_C");
   if (e && atoi(e) > 0) return (uint32_t)atoi(e);
+  // Precomputed bases: the stored multiples are 2^(k*c*Wf) P, so c must be the SAME when the table is built and every
+  // time it is used, whatever prefix length n the MSM runs over -- it may not depend on n.
+  if (factor > 1) return kPrecomputeWindow;
   if (g1 && factor <= 1 && bits >= 250 && n >= (1u << 11)) return n <= (1u << 17) ? 13u : 16u;
   double best = 1e300;
   uint32_t bc = 4;
@@ -323,6 +333,20 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
     constexpr int PB = pair_batch<F>::B;
     uint32_t* srcg = nullptr;
     F *preg = nullptr, *tot = nullptr;
+    // The slot-major scratch (stride nt = grid * PR_TPB) and the ping-pong point buffers are allocated once, for the
+    // LARGEST level.  That is level 0 while total > nbuckets + 2, but the bound (in + nbuckets) / 2 + 1 GROWS from level
+    // to level on a sparse input (forced B381_MSM_LEVELS with few points per bucket), so take the maximum over the plan.
+    size_t nt_max = 0, nt_buf[2] = {0, 0};        // scratch stride; point buffers of the even / odd levels
+    {
+      size_t in = total;
+      for (int l = 0; l < levels; l++) {
+        const size_t out = (in + sh.nbuckets) / 2 + 1;
+        const size_t nt_l = (size_t)grid_for(out, (size_t)PR_TPB * PB) * PR_TPB;
+        if (nt_l > nt_max) nt_max = nt_l;
+        if (nt_l > nt_buf[l & 1]) nt_buf[l & 1] = nt_l;
+        in = out;
+      }
+    }
     for (int l = 0; l < levels; l++) {
       const size_t max_out = (max_in + sh.nbuckets) / 2 + 1;
       uint32_t *half, *out_off;
@@ -335,12 +359,11 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
       B381_CUDA_TRY(sc.alloc(&stmp, sb));
       B381_CUDA_TRY(cub::DeviceScan::ExclusiveSum(stmp, sb, half, out_off, (int)sh.nbuckets + 1, st));
       const unsigned g = grid_for(max_out, (size_t)PR_TPB * PB);
-      const uint32_t nt = g * PR_TPB;
-      if (!buf[l & 1]) B381_CUDA_TRY(sc.alloc(&buf[l & 1], (size_t)nt * PB));   // ping-pong: sizes only shrink
-      if (!srcg) {                                                               // level 0 is the largest
-        B381_CUDA_TRY(sc.alloc(&srcg, (size_t)nt * PB));
-        B381_CUDA_TRY(sc.alloc(&preg, (size_t)nt * PB));
-        B381_CUDA_TRY(sc.alloc(&tot, (size_t)nt));
+      if (!buf[l & 1]) B381_CUDA_TRY(sc.alloc(&buf[l & 1], nt_buf[l & 1] * PB));   // ping-pong
+      if (!srcg) {
+        B381_CUDA_TRY(sc.alloc(&srcg, nt_max * PB));
+        B381_CUDA_TRY(sc.alloc(&preg, nt_max * PB));
+        B381_CUDA_TRY(sc.alloc(&tot, nt_max));
       }
       launch_pair_level<F>(l == 0, in_off, out_off, sh.nbuckets, l == 0 ? svals : nullptr,
                            l == 0 ? d_bases : buf[(l - 1) & 1], (size_t)n * factor, g, srcg, preg, tot, buf[l & 1], st);
@@ -409,8 +432,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
     const char* e = getenv("B381_ACC_MINB");
     if (e) variant = atoi(e);
     const unsigned g = grid_for(max_tasks, 128);
-    if (acc_vals && launch_lazy<F>(g, st, task_start + sh.nbuckets, tasks, svals, d_bases, partial, order)) {
-    } else if (variant == 3) k_msm_accumulate<F, 3><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, acc_vals, acc_pts, partial, order);
+    if (variant == 3) k_msm_accumulate<F, 3><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, acc_vals, acc_pts, partial, order);
     else if (variant == 4) k_msm_accumulate<F, 4><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, acc_vals, acc_pts, partial, order);
     else k_msm_accumulate<F, 1><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, acc_vals, acc_pts, partial, order);
   }
@@ -475,7 +497,18 @@ static int msm_entry(const fr_t* scalars, const affine_t<F>* bases, int msm_size
       return map_cuda_error(e);
     if ((e = stage_in(sc, bases, nbases, cfg->are_points_on_device, &d_bases)) != cudaSuccess)
       return map_cuda_error(e);
-    if (!cfg->are_points_montgomery_form && nbases) {
+    bool bases_mont = cfg->are_points_montgomery_form;
+    if (!bases_mont && factor > 1 && nbases) {
+      // precomputed bases: see k_points_form_probe (one 4-byte read-back; only on this flag combination)
+      int* d_flag;
+      int h_flag = 0;
+      if ((e = sc.alloc(&d_flag, 1)) != cudaSuccess) return map_cuda_error(e);
+      k_points_form_probe<F><<<1, 1, 0, st>>>(d_bases, (uint32_t)(nbases < 64 ? nbases : 64), d_flag);
+      if ((e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) return map_cuda_error(e);
+      if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return map_cuda_error(e);
+      bases_mont = h_flag != 0;
+    }
+    if (!bases_mont && nbases) {
       affine_t<F>* conv;
       if ((e = sc.alloc(&conv, nbases)) != cudaSuccess) return map_cuda_error(e);
       k_points_to_mont<F><<<grid_for(nbases, 128), 128, 0, st>>>(d_bases, conv, (uint32_t)nbases);
@@ -541,7 +574,7 @@ static int precompute_entry(const affine_t<F>* in, int bases_size, const b381_ms
     uint32_t c = cfg->c > 0 ? (uint32_t)cfg->c : pick_window(n, bits, factor, sizeof(F) == sizeof(fq_t));
     const msm_shape sh = make_msm_shape(n, c, bits, factor);
     uint32_t shift = c * sh.Wf;
-    if (n) k_precompute_bases<F><<<grid_for(n, 64), 64, 0, st>>>(d_in, d_out, n, factor, shift);
+    if (n) k_precompute_bases<F><<<grid_for(n, 64), 64, 0, st>>>(d_in, d_out, n, factor, shift, cfg->are_points_montgomery_form);
     if (!cfg->are_results_on_device) {
       e = cudaMemcpyAsync(out, d_out, sizeof(affine_t<F>) * (size_t)n * factor, cudaMemcpyDeviceToHost, st);
       if (e != cudaSuccess) return map_cuda_error(e);

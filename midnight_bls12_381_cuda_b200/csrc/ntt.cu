@@ -117,13 +117,29 @@ struct Domain {
   fr_t ninv[33];             // 2^-k, Montgomery
   std::vector<CosetTable> cosets;
 };
-static Domain g_dom;
+// One domain PER DEVICE (ICICLE's set_device model: a single process may drive several GPUs; twiddles built on
+// device 0 are not addressable from device 1).  Every entry point works on the calling thread's current device.
+static std::map<int, Domain> g_doms;
 static std::mutex g_dom_mu;
+static thread_local int g_ntt_last_info[4] = {0, 0, 0, 0};   // passes, log n, batch, tiles of the last pass
+
+// caller holds g_dom_mu
+static Domain& cur_domain() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  Domain& d = g_doms[dev];
+  d.device = dev;
+  return d;
+}
+#define g_dom (cur_domain())
 
 static void release_locked() {
-  if (g_dom.table) cudaFree(g_dom.table);
-  for (auto& c : g_dom.cosets) cudaFree(c.dev);
-  g_dom = Domain();
+  Domain& d = cur_domain();
+  if (d.table) cudaFree(d.table);
+  for (auto& c : d.cosets) cudaFree(c.dev);
+  const int dev = d.device;
+  d = Domain();
+  d.device = dev;
 }
 
 static int init_domain(const fr_t& root, cudaStream_t st) {
@@ -151,7 +167,6 @@ static int init_domain(const fr_t& root, cudaStream_t st) {
   e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { cudaFree(table); return map_cuda_error(e); }
-  cudaGetDevice(&g_dom.device);
   g_dom.K = K;
   g_dom.root_mont = h.root_mont;
   g_dom.table = table;
@@ -193,7 +208,9 @@ static int coset_table(const fr_t& gen, uint32_t n, bool inverse, cudaStream_t s
     if (e != cudaSuccess) { cudaFree(dev); return map_cuda_error(e); }
   }
   k_fr_powers<<<grid_for((N + 63) / 64, 128), 128, 0, st>>>(g, base, N, dev);
-  if (cudaGetLastError() != cudaSuccess) { cudaFree(dev); return B381_UNKNOWN_ERROR; }
+  // The table is published to every stream through the cache, so it must be COMPLETE before it becomes visible: a
+  // cache hit on another stream has no dependency on `st`.  Builds are rare (once per generator and size).
+  if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) { cudaFree(dev); return B381_UNKNOWN_ERROR; }
   g_dom.cosets.push_back(CosetTable{gen, n, inverse, dev});
   *out = dev;
   return B381_SUCCESS;
@@ -274,6 +291,7 @@ static int ntt_run(const fr_t* input, int size, int dir, const b381_ntt_config* 
       const size_t smem = (size_t)2 * sizeof(uint4) << tile_log;
       launch_ntt_pass(p, src, dst, (unsigned)tiles, smem, st);
     }
+    g_ntt_last_info[0] = (int)P; g_ntt_last_info[1] = (int)n; g_ntt_last_info[2] = (int)batch;
     lk.unlock();   // tables stay valid: release_domain synchronises the device before freeing
     if ((e = cudaGetLastError()) != cudaSuccess) return map_cuda_error(e);
     if (!cfg->are_outputs_on_device) {
@@ -389,6 +407,11 @@ int b381_ntt_get_rou_from_domain(uint64_t logn, b381_fr* rou) {
   }
   memcpy(rou, &v, sizeof(v));
   return B381_SUCCESS;
+}
+int b381_ntt_last_info(int* out, int cap) {
+  int k = 0;
+  for (; k < cap && k < 4; k++) out[k] = g_ntt_last_info[k];
+  return k;
 }
 b381_ntt_config b381_default_ntt_config(void) {
   b381_ntt_config c;

@@ -54,18 +54,13 @@ __global__ void __launch_bounds__(128) k_jac_to_affine(const jacobian_t<F>* in, 
   }
 }
 
-template <class F> B381_DI F curve_b();
-template <> B381_DI fq_t curve_b<fq_t>() { fq_t two = dbl(one<fq_t>()); return dbl(two); }          // b = 4
-template <> B381_DI fq2_t curve_b<fq2_t>() { fq_t f = curve_b<fq_t>(); return fq2_t{f, f}; }        // b' = 4(1 + u)
-
 // flags[i] = 1 when y^2 = x^3 + b or the point is infinity, else 0
 template <class F>
 __global__ void __launch_bounds__(256) k_on_curve(const affine_t<F>* in, uint64_t n, uint8_t* flags) {
   uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   affine_t<F> p = in[i];
-  bool ok = is_inf(p) || eq(sqr(p.y), add(mul(sqr(p.x), p.x), curve_b<F>()));
-  flags[i] = ok ? 1 : 0;
+  flags[i] = on_curve(p) ? 1 : 0;
 }
 
 enum PointOp { P_TO_JAC = 0, P_TO_AFFINE = 1, P_ON_CURVE = 2 };

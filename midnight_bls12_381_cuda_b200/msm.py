@@ -21,7 +21,12 @@ class MsmError(RuntimeError):
 
 
 class PrecomputedBases:
-    """core/msm.rs:174-262: device-resident bases, optionally expanded by precompute_factor."""
+    """core/msm.rs:174-262: device-resident bases, optionally expanded by precompute_factor.
+
+    Precomputed buffers hold point i's multiples interleaved at [i*factor + k] (upstream ICICLE's layout), so an MSM
+    over fewer scalars than original_size uses a prefix of the same buffer, as core/msm.rs:654-661 expects.  `window`
+    is the cfg.c the table was built with (0 = the backend's fixed default for precomputed bases); every MSM over these
+    bases is issued with the same value, whatever the context's own window is."""
 
     def __init__(self, buffer: DeviceVec, size: int, factor: int = 1, window: int = 0):
         self.buffer, self._size, self._factor, self.window = buffer, size, factor, window
@@ -127,25 +132,21 @@ class GpuMsmContext:
         sc = TypeConverter.scalar_slice_as_icicle(scalars)
         bases.required_size_for_scalars(sc.shape[0])
         res = np.zeros(18, dtype=np.uint64)
-        cfg = self._cfg(points_on_device=True)
-        cfg.precompute_factor = bases.factor()
+        cfg = self._cfg_for(bases, points_on_device=True)
         n = sc.shape[0]
-        if bases.is_precomputed() and n != bases.original_size():
-            raise MsmError("precomputed bases need scalars.len() == original_size (block stride)")
         self._check(L.lib().b381_g1_msm(L.ptr(sc), L.ptr(bases.buffer), n, C.byref(cfg), L.ptr(res)), "msm")
         return TypeConverter.icicle_to_g1_projective(res)
 
     def msm_with_device_bases_async(self, scalars, bases: PrecomputedBases) -> MsmHandle:
         sc = np.ascontiguousarray(TypeConverter.scalar_slice_as_icicle(scalars))
         bases.required_size_for_scalars(sc.shape[0])
+        # host scalars go straight into the plugin call: it stages them on THIS call's stream from the stream-ordered
+        # pool (no cudaMalloc/cudaFree, no device-wide sync), so two handles in flight overlap copy and compute
         st = ManagedStream.create()
-        d_sc = DeviceVec(sc.shape[0], 32)
-        L.check(L.lib().b381_copy_to_device_async(L.ptr(d_sc), L.ptr(sc), sc.nbytes, st.handle), "h2d")
         res = np.zeros(18, dtype=np.uint64)
-        cfg = self._cfg(points_on_device=True, scalars_on_device=True, stream=st, is_async=True)
-        cfg.precompute_factor = bases.factor()
-        self._check(L.lib().b381_g1_msm(L.ptr(d_sc), L.ptr(bases.buffer), sc.shape[0], C.byref(cfg), L.ptr(res)), "msm")
-        return MsmHandle(st, res, (sc, d_sc, bases))
+        cfg = self._cfg_for(bases, points_on_device=True, stream=st, is_async=True)
+        self._check(L.lib().b381_g1_msm(L.ptr(sc), L.ptr(bases.buffer), sc.shape[0], C.byref(cfg), L.ptr(res)), "msm")
+        return MsmHandle(st, res, (sc, bases))
 
     def msm_async(self, scalars, points) -> MsmHandle:
         return self.msm_with_device_bases_async(scalars, self.upload_g1_bases(points))
@@ -156,22 +157,21 @@ class GpuMsmContext:
         b, n = sc.shape[0], sc.shape[1]
         bases.required_size_for_scalars(n)
         res = np.zeros((b, 18), dtype=np.uint64)
-        cfg = self._cfg(points_on_device=True)
-        cfg.batch_size, cfg.are_points_shared_in_batch, cfg.precompute_factor = b, True, bases.factor()
+        cfg = self._cfg_for(bases, points_on_device=True)
+        cfg.batch_size, cfg.are_points_shared_in_batch = b, True
         self._check(L.lib().b381_g1_msm(L.ptr(sc), L.ptr(bases.buffer), n, C.byref(cfg), L.ptr(res)), "msm batch")
         return [TypeConverter.icicle_to_g1_projective(r) for r in res]
 
     def msm_batch_with_device_bases_async(self, scalars_batch, bases: PrecomputedBases) -> BatchMsmHandle:
         sc = np.ascontiguousarray(np.stack([TypeConverter.scalar_slice_as_icicle(s) for s in scalars_batch]))
         b, n = sc.shape[0], sc.shape[1]
+        bases.required_size_for_scalars(n)
         st = ManagedStream.create()
-        d_sc = DeviceVec(b * n, 32)
-        L.check(L.lib().b381_copy_to_device_async(L.ptr(d_sc), L.ptr(sc), sc.nbytes, st.handle), "h2d")
         res = np.zeros((b, 18), dtype=np.uint64)
-        cfg = self._cfg(points_on_device=True, scalars_on_device=True, stream=st, is_async=True)
-        cfg.batch_size, cfg.are_points_shared_in_batch, cfg.precompute_factor = b, True, bases.factor()
-        self._check(L.lib().b381_g1_msm(L.ptr(d_sc), L.ptr(bases.buffer), n, C.byref(cfg), L.ptr(res)), "msm batch")
-        return BatchMsmHandle(st, res, (sc, d_sc, bases))
+        cfg = self._cfg_for(bases, points_on_device=True, stream=st, is_async=True)
+        cfg.batch_size, cfg.are_points_shared_in_batch = b, True
+        self._check(L.lib().b381_g1_msm(L.ptr(sc), L.ptr(bases.buffer), n, C.byref(cfg), L.ptr(res)), "msm batch")
+        return BatchMsmHandle(st, res, (sc, bases))
 
     # -- G2 ------------------------------------------------------------------
     def g2_msm(self, scalars, points):
@@ -195,12 +195,10 @@ class GpuMsmContext:
         sc = np.ascontiguousarray(TypeConverter.scalar_slice_as_icicle(scalars))
         d_pts = self.upload_g2_bases(points)
         st = ManagedStream.create()
-        d_sc = DeviceVec(sc.shape[0], 32)
-        L.check(L.lib().b381_copy_to_device_async(L.ptr(d_sc), L.ptr(sc), sc.nbytes, st.handle), "h2d")
         res = np.zeros(36, dtype=np.uint64)
-        cfg = self._cfg(points_on_device=True, scalars_on_device=True, stream=st, is_async=True)
-        self._check(L.lib().b381_g2_msm(L.ptr(d_sc), L.ptr(d_pts), sc.shape[0], C.byref(cfg), L.ptr(res)), "g2 msm")
-        return G2MsmHandle(st, res, (sc, d_sc, d_pts))
+        cfg = self._cfg(points_on_device=True, stream=st, is_async=True)
+        self._check(L.lib().b381_g2_msm(L.ptr(sc), L.ptr(d_pts), sc.shape[0], C.byref(cfg), L.ptr(res)), "g2 msm")
+        return G2MsmHandle(st, res, (sc, d_pts))
 
     def warmup(self) -> float:
         """core/msm.rs:931-983: one tiny MSM to pay context/module load once; returns seconds."""
@@ -221,6 +219,14 @@ class GpuMsmContext:
         cfg.is_async = is_async
         if stream is not None:
             cfg.stream = stream.handle
+        return cfg
+
+    def _cfg_for(self, bases: PrecomputedBases, **kw):
+        """config of an MSM over `bases`: precomputed tables fix the factor AND the window they were built with."""
+        cfg = self._cfg(**kw)
+        cfg.precompute_factor = bases.factor()
+        if bases.is_precomputed():
+            cfg.c = bases.window
         return cfg
 
     @staticmethod

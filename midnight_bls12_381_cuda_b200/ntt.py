@@ -53,7 +53,8 @@ class NttHandle:
 
 
 _domain_lock = threading.Lock()
-_domain_log = 0
+_domain_log = 0            # device 0 (kept as a plain int: tests reset it)
+_domain_logs: dict[int, int] = {}   # other devices: the backend keeps one domain per device
 
 
 class GpuNttContext:
@@ -64,25 +65,30 @@ class GpuNttContext:
         except Exception as e:  # noqa: BLE001
             raise NttError(f"backend init failed: {e}") from e
         self._max_log = max_log_size
+        self.device_id = device_id
         self.ordering = ordering
-        self._ensure_domain_initialized(max_log_size)
+        self._ensure_domain_initialized(max_log_size, device_id)
 
     @staticmethod
-    def _ensure_domain_initialized(k: int) -> None:
-        """core/ntt.rs:380-442: one process-wide domain, grown on demand."""
+    def _ensure_domain_initialized(k: int, device_id: int = 0) -> None:
+        """core/ntt.rs:380-442: one domain per device (the current device's), grown on demand."""
         global _domain_log
         with _domain_lock:
-            if _domain_log >= k:
+            have = _domain_log if device_id == 0 else _domain_logs.get(device_id, 0)
+            if have >= k:
                 return
             lib = L.lib()
-            if _domain_log:
+            if have:
                 lib.b381_ntt_release_domain()
             root = get_root_of_unity(1 << k)
             cfg = L.NTTInitDomainConfig()
             code = lib.b381_ntt_init_domain(L.ptr(root), C.byref(cfg))
             if code != 0:
                 raise NttError(f"init_domain(2^{k}): {L.ERROR_NAMES.get(code, code)}")
-            _domain_log = k
+            if device_id == 0:
+                _domain_log = k
+            else:
+                _domain_logs[device_id] = k
 
     def max_log_size(self) -> int:
         return self._max_log

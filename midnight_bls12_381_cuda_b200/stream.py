@@ -73,10 +73,17 @@ class DeviceVec:
     """Owned device buffer of `count` elements of `elem_bytes` bytes."""
 
     def __init__(self, count: int, elem_bytes: int):
-        self.count, self.elem_bytes = count, elem_bytes
+        self.count, self.elem_bytes, self._owned = count, elem_bytes, True
         p = C.c_void_p()
         L.check(L.lib().b381_malloc(C.byref(p), max(1, count * elem_bytes)), "device_malloc")
         self.ptr = p.value
+
+    @classmethod
+    def borrow(cls, ptr: int, count: int, elem_bytes: int) -> "DeviceVec":
+        """non-owning view of device memory somebody else allocated (a torch tensor, an ICICLE DeviceSlice)"""
+        v = cls.__new__(cls)
+        v.count, v.elem_bytes, v.ptr, v._owned = count, elem_bytes, ptr, False
+        return v
 
     @classmethod
     def from_host(cls, arr: np.ndarray, elem_bytes: int) -> "DeviceVec":
@@ -107,9 +114,9 @@ class DeviceVec:
         return out
 
     def free(self) -> None:
-        if self.ptr:
+        if self.ptr and self._owned:
             L.lib().b381_free(C.c_void_p(self.ptr))
-            self.ptr = 0
+        self.ptr = 0
 
     def __del__(self):
         try:

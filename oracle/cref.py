@@ -37,6 +37,10 @@ def _u64(a, shape=None):
     return a if shape is None else a.reshape(shape)
 
 
+def set_threads(n: int) -> None:
+    lib().orc_set_threads(int(n))
+
+
 def num_threads() -> int:
     return lib().orc_num_threads()
 
@@ -140,6 +144,14 @@ def coset_ntt(a, g, inverse=False):
     log_n = (a.shape[0]).bit_length() - 1
     assert lib().orc_coset_ntt(_p(a), log_n, int(inverse), _p(g)) == 0
     return a
+
+
+def poly_eval(a, z):
+    """sum_j a[j] z^j (a: (n,4) Montgomery, z: Montgomery limbs) -> Montgomery limbs; Horner, no NTT code involved."""
+    a, z = _u64(a), _u64(z)
+    out = np.zeros(4, dtype=np.uint64)
+    lib().orc_fr_poly_eval(_p(a), C.c_size_t(a.size // 4), _p(z), _p(out))
+    return out
 
 
 def bit_reverse(a):

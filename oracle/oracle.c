@@ -451,12 +451,39 @@ int orc_coset_ntt(u64* a, int log_n, int inverse, const u64* g) {
   if (!inverse) return orc_ntt(a, log_n, 0);
   return 0;
 }
+/* sum_j a[j] z^j by Horner over per-thread chunks (a, z, out Montgomery).  Shares no code with orc_ntt: the tests
+ * use it to re-evaluate single NTT outputs y[i] = A(omega^i) at sizes where a Python loop is out of reach. */
+void orc_fr_poly_eval(const u64* a, size_t n, const u64* z, u64* out) {
+  const size_t CH = (size_t)1 << 16;
+  const size_t chunks = (n + CH - 1) / CH;
+  u64* part = (u64*)malloc(chunks * 32);
+#pragma omp parallel for schedule(static)
+  for (long c = 0; c < (long)chunks; c++) {
+    size_t lo = (size_t)c * CH, hi = lo + CH < n ? lo + CH : n;
+    u64 acc[4] = {0, 0, 0, 0};
+    for (size_t j = hi; j-- > lo;) { mont_mul(acc, acc, z, &FR); mod_add(acc, acc, a + 4 * j, &FR); }
+    memcpy(part + 4 * c, acc, 32);
+  }
+  u64 zc[4], acc[4] = {0, 0, 0, 0};
+  fr_pow_u64(zc, z, (u64)CH);
+  for (size_t c = chunks; c-- > 0;) { mont_mul(acc, acc, zc, &FR); mod_add(acc, acc, part + 4 * c, &FR); }
+  memcpy(out, acc, 32);
+  free(part);
+}
 void orc_bit_reverse(u64* a, int log_n) {
   const size_t n = (size_t)1 << log_n;
   for (size_t i = 0; i < n; i++) {
     size_t j = bitrev(i, log_n);
     if (i < j) { u64 t[4]; memcpy(t, a + 4 * i, 32); memcpy(a + 4 * i, a + 4 * j, 32); memcpy(a + 4 * j, t, 32); }
   }
+}
+/* torchrun exports OMP_NUM_THREADS=1 to its workers; bench.py --impl reference asks for every core explicitly */
+void orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
 }
 int orc_num_threads(void) {
 #ifdef _OPENMP

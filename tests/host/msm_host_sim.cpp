@@ -26,11 +26,11 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint
   if (factor > 1) {
     std::vector<affine_t<F>> ex((size_t)n * factor);
     for (uint32_t i = 0; i < n; i++) {
-      ex[i] = pts[i];
+      ex[(size_t)i * factor] = pts[i];
       xyzz_t<F> acc = to_xyzz(pts[i]);
       for (uint32_t k = 1; k < factor; k++) {
         for (uint32_t b = 0; b < c * sh.Wf; b++) acc = xyzz_dbl(acc);
-        ex[(size_t)k * n + i] = xyzz_to_affine(acc);
+        ex[(size_t)i * factor + k] = xyzz_to_affine(acc);
       }
     }
     pts.swap(ex);

@@ -248,11 +248,63 @@ def test_batch_and_precompute(cuda, b381, oracle):
     for r, s in zip(res, singles):
         assert r[0].to_bytes(48, "little") + r[1].to_bytes(48, "little") == s[:96]
     assert ctx.msm_batch_with_device_bases_async([mont(sc[i * n:(i + 1) * n]) for i in range(b)], dev).wait() == res
+    short = oracle.msm(1, sc[:777], bases[:777]).tobytes()
     for factor in (2, 4):
         pre = ctx.precompute_bases(dev, factor)
         assert pre.buffer_size() == n * factor and pre.is_precomputed()
         r = ctx.msm_with_device_bases(mont(sc[:n]), pre)
         assert r[0].to_bytes(48, "little") + r[1].to_bytes(48, "little") == singles[0][:96]
+        # fewer scalars than bases over the FULL precomputed buffer (core/msm.rs:654-661), every entry point;
+        # a context with another window must still use the table's own
+        other = M.GpuMsmContext(window=11)
+        for got in (ctx.msm_with_device_bases(mont(sc[:777]), pre), other.msm_with_device_bases(mont(sc[:777]), pre),
+                    ctx.msm_with_device_bases_async(mont(sc[:777]), pre).wait(),
+                    ctx.msm_batch_with_device_bases([mont(sc[:777])], pre)[0],
+                    ctx.msm_batch_with_device_bases_async([mont(sc[:777])], pre).wait()[0]):
+            assert got[0].to_bytes(48, "little") + got[1].to_bytes(48, "little") == short[:96]
+
+
+def test_precompute_flag_combinations(cuda, b381, oracle):
+    """The reference's Rust layer builds precomputed tables with are_bases_montgomery_form = true and uses them with
+    false (core/msm.rs:450 vs :641-643); upstream ICICLE writes the table in the form declared for the input.  Both
+    must give the right commitment, for Montgomery and for standard-form input points, on host and device buffers."""
+    import torch
+    lib = b381.lib()
+    n, factor = 1500, 3
+    bases = oracle.gen_series(1, [5, 0, 0, 0], [3, 0, 0, 0], n)          # Montgomery affine
+    bases_std = np.stack([np.concatenate([oracle.unop("fq_from_mont", p[:6], 6), oracle.unop("fq_from_mont", p[6:], 6)])
+                          for p in bases])
+    sc = oracle.random_fr(31, n)
+    exp = oracle.msm(1, sc, bases).tobytes()
+    for src, declared_mont in ((bases, True), (bases_std, False)):
+        cfg = lib.b381_default_msm_config()
+        cfg.precompute_factor, cfg.are_points_montgomery_form = factor, declared_mont
+        table = np.zeros((n * factor, 12), dtype=np.uint64)
+        assert lib.b381_g1_msm_precompute_bases(b381.ptr(src), n, C.byref(cfg), b381.ptr(table)) == 0
+        assert (table[::factor] == src).all()                             # multiple 0 is the point itself, same form
+        d_table = torch.from_numpy(table.view(np.int64)).cuda()
+        for use_flag in (declared_mont, False):
+            for buf, on_dev in ((table, False), (d_table, True)):
+                m = lib.b381_default_msm_config()
+                m.precompute_factor, m.are_points_montgomery_form, m.are_points_on_device = factor, use_flag, on_dev
+                res = np.zeros(18, dtype=np.uint64)
+                assert lib.b381_g1_msm(b381.ptr(sc), b381.ptr(buf), n, C.byref(m), b381.ptr(res)) == 0
+                assert res.tobytes() == exp, (declared_mont, use_flag, on_dev)
+
+
+def test_forced_levels_on_sparse_buckets(cuda, b381, oracle, monkeypatch):
+    """Affine levels forced onto an input with fewer points than buckets (c = 16, n = 1000): the per-level bound
+    (in + nbuckets) / 2 + 1 GROWS from level to level there, so the slot-major scratch must be sized for the largest
+    planned level, not for level 0 (out-of-bounds write otherwise)."""
+    n = 1000
+    bases = oracle.gen_series(1, [2, 0, 0, 0], [9, 0, 0, 0], n)
+    sc = oracle.random_fr(77, n)
+    exp = oracle.msm(1, sc, bases).tobytes()
+    for levels in ("1", "3", "5"):
+        monkeypatch.setenv("B381_MSM_LEVELS", levels)
+        assert raw_msm(b381, "g1", sc, bases, n, c=16).tobytes() == exp, levels
+        assert raw_msm(b381, "g1", sc, bases, n, c=10).tobytes() == exp, levels
+    monkeypatch.delenv("B381_MSM_LEVELS")
 
 
 def test_full_size_discrete_log_check(cuda, b381, oracle):

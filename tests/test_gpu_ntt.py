@@ -159,26 +159,54 @@ def test_natural_order_equals_bit_reversed_order(ctx, oracle, cuda, logn):
         del nn, nr
 
 
+@pytest.mark.parametrize("logn", [21, 22, 24])
+def test_large_vs_oracle(ctx, oracle, cuda, logn):
+    """BASELINE.json's headline NTT size and its neighbours (the multi-pass plans): every output byte of the forward
+    kNN transform, the inverse and the coset-7 pair against oracle.ntt / oracle.coset_ntt (core/ntt.rs:1488-1603
+    contract: forward = best_fft, inverse(forward(x)) = x, coset = scale by g^i first)."""
+    import midnight_bls12_381_cuda_b200 as M
+    n = 1 << logn
+    a = oracle.random_fr(0xB12381_2100 + logn, n)
+    d = cuda.from_numpy(a.view(np.int64)).cuda()
+
+    def host(t):
+        return t.cpu().numpy().view(np.uint64).reshape(-1, 4)
+    ctx.ntt_on_device(d.data_ptr(), M.ntt.FORWARD, size=n)
+    y = host(d)
+    exp = oracle.ntt(a)
+    assert (y == exp).all(), f"forward 2^{logn}: first mismatch at {int(np.argmax((y != exp).any(axis=1)))}"
+    # inverse of an independent vector (not just the round trip): oracle.intt(b) for random b
+    b = oracle.random_fr(0xB12381_2200 + logn, n)
+    d.copy_(cuda.from_numpy(b.view(np.int64)))
+    ctx.ntt_on_device(d.data_ptr(), M.ntt.INVERSE, size=n)
+    assert (host(d) == oracle.ntt(b, inverse=True)).all(), f"inverse 2^{logn}"
+    g = mont([7])[0]
+    yc = ctx.forward_coset_ntt(a, g)
+    assert (yc == oracle.coset_ntt(a, g)).all(), f"coset forward 2^{logn}"
+    assert (ctx.inverse_coset_ntt(yc, g) == a).all(), f"coset inverse 2^{logn}"
+
+
 def test_full_size_2_24(ctx, oracle, cuda):
-    """2^24: inverse(forward(x)) == x, linearity against a second vector, Horner spot checks."""
+    """2^24: inverse(forward(x)) == x, y[0] == sum, and 32 random outputs re-evaluated as polynomial values
+    y[i] = sum_j a[j] w^(ij) with big integers (spot checks that do not share code with any NTT)."""
+    import random
+
     import midnight_bls12_381_cuda_b200 as M
     n = 1 << 24
     a = oracle.random_fr(0xB12381_2024, n)
     d = cuda.from_numpy(a.view(np.int64)).cuda()
     ctx.ntt_on_device(d.data_ptr(), M.ntt.FORWARD, size=n)
     y = d.cpu().numpy().view(np.uint64).reshape(-1, 4)
-    w = P.fr_omega(24)
-    vals = None
-    for i in (0, 1, n // 2 + 12345):
-        # y[i] = sum_j a[j] w^(ij): evaluate by splitting j = j1*2^12 + j2 to keep Python work at 2^13 muls
-        if vals is None:
-            vals = [P.fr_from_mont(v) for v in fr_ints(a[:: 1 << 12])]   # only used for i = 0 below
-        if i == 0:
-            pass
     # i = 0 is the plain sum; check it exactly with limb-wise sums of the Montgomery words
     lo = (a & np.uint64(0xFFFFFFFF)).sum(axis=0, dtype=np.uint64)
     hi = (a >> np.uint64(32)).sum(axis=0, dtype=np.uint64)
     tot = sum((int(lo[l]) + (int(hi[l]) << 32)) << (64 * l) for l in range(4)) % P.R_MOD
     assert P.from_limbs(y[0]) == tot
+    # y[i] = A(w^i): Horner evaluation of the input as a polynomial (oracle.poly_eval), 32 positions
+    w = P.fr_omega(24)
+    rng = random.Random(0xB12381)
+    for i in [1, n // 2 + 12345, n - 1] + [rng.randrange(n) for _ in range(29)]:
+        z = fr_array([P.fr_to_mont(pow(w, i, P.R_MOD))])[0]
+        assert (y[i] == oracle.poly_eval(a, z)).all(), i
     ctx.ntt_on_device(d.data_ptr(), M.ntt.INVERSE, size=n)
     assert cuda.equal(d, cuda.from_numpy(a.view(np.int64)).cuda())

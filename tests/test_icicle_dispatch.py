@@ -1,0 +1,42 @@
+"""The ICICLE registration path end to end: a mock of ICICLE's frontend, built from the
+reference's own headers (bls12-381/include/icicle_backend_api.cuh:118-225, include/icicle/device_api.h:54-227), is loaded
+before the three backend libraries; their static initialisers register "CUDA" with it and the test calls the stored
+std::function callbacks / DeviceAPI virtuals.  Each case runs in a fresh process because registration happens once, at
+dlopen time (tests/icicle_dispatch_driver.py)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MOCK = os.path.join(ROOT, "oracle", "_ref", "libicicle_mock.so")
+
+
+def run(mode):
+    if not os.path.exists(MOCK):
+        pytest.skip("oracle/_ref/libicicle_mock.so not built (needs /root/reference at build time: make -C oracle mock)")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "icicle_dispatch_driver.py"), mode],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def test_every_callback_registers_with_the_reference_prototypes(b381):
+    """no GPU needed: all 11 register_* imports + register_deviceAPI resolve against definitions mangled from the
+    reference's header, and the G2 getters (g2_registry.cu:84-101) hand the G2 callbacks out."""
+    res = run("registration")
+    assert res["mask"] == 0xFFF, bin(res["mask"])
+    assert res["g2"] == 7          # msm + precompute present for "CUDA", empty std::function for an unknown device type
+
+
+@pytest.mark.gpu
+def test_registered_callbacks_compute(cuda, b381, oracle):
+    res = run("compute")
+    assert res["mask"] == 0xFFF and res["g2"] == 7
+    for key in ("g1_msm", "g1_precompute", "g2_msm", "g2_precompute", "ntt_init", "ntt_forward", "ntt_inverse", "ntt_rou",
+                "ntt_release", "vecops", "dev_count", "dev_set", "dev_memory_and_streams"):
+        assert res[key] is True, (key, res)
+    assert res["ntt_after_release"] == 11
+    assert res["dev_properties"] == [0, 0, 1, 1]      # using_host_memory, num_memory_regions, pinned (cuda_device_api.cu:141-147)

@@ -151,3 +151,25 @@ def test_vecops_golden(oracle):
         assert [hex(x) for x in fr_ints(oracle.vecop(op, a, b))] == v[name]
     assert [hex(x) for x in fr_ints(oracle.vecop(2, a[0], b, a_scalar=True))] == v["scalar_mul"]
     assert [hex(x) for x in fr_ints(oracle.vecop(0, a[0], b, a_scalar=True))] == v["scalar_add"]
+
+
+def test_poly_eval_pins_ntt_outputs(oracle):
+    """oracle.poly_eval (Horner, shares no code with orc_ntt) against big integers and against single NTT outputs:
+    y[i] = A(omega^i).  The GPU tests use it for spot checks at 2^24."""
+    n = 1 << 10
+    a = oracle.random_fr(99, n)
+    ai = [P.fr_from_mont(v) for v in fr_ints(a)]
+    y = oracle.ntt(a)
+    w = P.fr_omega(10)
+    for i in (0, 1, 517, n - 1):
+        z = pow(w, i, P.R_MOD)
+        got = oracle.poly_eval(a, mont([z])[0])
+        assert P.fr_from_mont(P.from_limbs(got)) == sum(c * pow(z, j, P.R_MOD) for j, c in enumerate(ai)) % P.R_MOD
+        assert (got == y[i]).all()
+    # chunked path (n > 2^16) against the transform
+    n = 1 << 18
+    a = oracle.random_fr(100, n)
+    y = oracle.ntt(a)
+    w = P.fr_omega(18)
+    for i in (3, n // 2 + 1, n - 1):
+        assert (oracle.poly_eval(a, mont([pow(w, i, P.R_MOD)])[0]) == y[i]).all()

@@ -24,7 +24,7 @@ from __future__ import annotations
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "..", "..", "midnight_bls12_381_cuda_b200", "csrc", "gen"))
 from ptxir import Block, M32  # noqa: E402
 
 BLS_X = -0xD201000000010000
@@ -306,7 +306,7 @@ def generate() -> str:
 
 
 if __name__ == "__main__":
-    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "fq_unsat.cuh")
+    dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fq_unsat.cuh")
     with open(dst, "w") as fh:
         fh.write(generate())
     for n in ROUTINES:

@@ -5,7 +5,8 @@ import os
 import random
 import sys
 
-sys.path.insert(0, os.path.join(os.path.dirname(__file__), "..", "midnight_bls12_381_cuda_b200", "csrc", "gen"))
+_ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), "..", "..", ".."))
+sys.path[:0] = [os.path.dirname(os.path.abspath(__file__)), _ROOT]
 import gen_unsat as U  # noqa: E402
 
 from oracle import pyref as P  # noqa: E402
@@ -61,7 +62,7 @@ def test_wire_conversions_and_zero_test():
 
 
 def test_generated_header_is_current():
-    here = os.path.join(os.path.dirname(__file__), "..", "midnight_bls12_381_cuda_b200", "csrc", "fq_unsat.cuh")
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "fq_unsat.cuh")
     assert open(here).read() == U.generate()
 
 
