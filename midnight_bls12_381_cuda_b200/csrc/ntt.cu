@@ -15,52 +15,128 @@
 namespace b381 {
 
 constexpr uint32_t kTile = 1u << kNttTileLog;
-constexpr uint32_t kNttThreads = 256;
-constexpr uint32_t kMaxDomainLog = 28;            // 2^28 - 1 twiddles = 8 GiB; larger roots are refused
+constexpr uint32_t kMaxDomainLog = 27;            // two tables of 2^27 - 1 twiddles = 8 GiB; larger roots are refused
 
 // ------------------------------------------------------------------ kernels
-// RMAX = stages per register-blocked step: 1 = one butterfly stage per trip through shared memory,
-// 2 = radix-4 steps (4 elements in registers), 3 = radix-8 steps (8 elements, 128 registers, 2 CTAs/SM).
-template <int RMAX>
-__global__ void __launch_bounds__(kNttThreads, RMAX == 3 ? 2 : 3) k_ntt_pass(ntt_pass_params p, const fr_t* in, fr_t* out) {
+// One pass = one kernel: tile load, (S + 1) / 2 register-blocked steps with a CTA barrier after each, tile store.
+// S (stages of the pass) and the tile geometry are template parameters, so every slot / twiddle index in the steps is
+// shifts and masks by constants:
+//   LO0 = true : last pass (lo = 0): contiguous 2^TL-element tile = 2^(TL-S) blocks of 2^S, no adjacent-column bits;
+//   LO0 = false: upper pass: 2^S rows x 2^(TL-S) adjacent columns.
+// NT threads per CTA, MINB CTAs per SM (register cap via __launch_bounds__).
+template <int S, bool LO0, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_ntt(const __grid_constant__ ntt_pass_params p, const fr_t* in, fr_t* out) {
   extern __shared__ uint4 smem[];
-  ntt_tile t;
-  const uint32_t tile_elems = 1u << (p.S + p.g + p.x);
-  t.lo = smem;
-  t.hi = smem + tile_elems;
+  const ntt_tile t{smem, smem + kTile};
   const uint64_t tile_id = p.tile_rot ? (blockIdx.x + p.tile_rot) % gridDim.x : blockIdx.x;
-  for (uint32_t pos = threadIdx.x; pos < tile_elems; pos += blockDim.x) ntt_tile_load(p, tile_id, pos, in, t);
+  const ntt_tile_ctx c = ntt_tile_begin(p, tile_id, (uint32_t)S, LO0 ? 0u : (uint32_t)(kNttTileLog - S),
+                                        LO0 ? (uint32_t)(kNttTileLog - S) : 0u, LO0 ? 0u : p.lo);
+#pragma unroll 2
+  for (uint32_t pos = threadIdx.x; pos < kTile; pos += NT) ntt_tile_load(p, c, pos, in, t);
   __syncthreads();
-  uint32_t s = p.S;
-  while (s > 0) {
-    const uint32_t R = s >= (uint32_t)RMAX ? (uint32_t)RMAX : s;
-    s -= R;
-    const uint32_t groups = tile_elems >> R;
-    for (uint32_t q = threadIdx.x; q < groups; q += blockDim.x) {
-      if (RMAX >= 3 && R == 3) ntt_tile_stages<3>(p, tile_id, q, s, t);
-      else if (RMAX >= 2 && R == 2) ntt_tile_stages<2>(p, tile_id, q, s, t);
-      else ntt_tile_stages<1>(p, tile_id, q, s, t);
+  constexpr uint32_t STEPS = (S + 1) / 2;
+#pragma unroll
+  for (uint32_t step = 0; step < STEPS; step++) {
+    uint32_t rl, s;
+    ntt_pass_step(S, step, &rl, &s);
+    if (rl == 1) {
+#pragma unroll 1
+      for (uint32_t q = threadIdx.x; q < kTile / 2; q += NT) ntt_step_r2(p, c, q, s, t);
+    } else if (LO0 && s == 0) {
+#pragma unroll 1
+      for (uint32_t q = threadIdx.x; q < kTile / 4; q += NT) ntt_step_r4<true>(p, c, q, s, t);
+    } else {
+#pragma unroll 1
+      for (uint32_t q = threadIdx.x; q < kTile / 4; q += NT) ntt_step_r4<false>(p, c, q, s, t);
     }
     __syncthreads();
   }
-  for (uint32_t pos = threadIdx.x; pos < tile_elems; pos += blockDim.x) ntt_tile_store(p, tile_id, pos, out, t);
+#pragma unroll 2
+  for (uint32_t pos = threadIdx.x; pos < kTile; pos += NT) ntt_tile_store(p, c, pos, out, t);
 }
 
-static int ntt_rmax() {
-  static const int r = [] { const char* e = getenv("B381_NTT_R"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v > 3 ? 3 : v; }();
-  return r;
+// Same pass with every shape parameter at run time: tiles smaller than 2^TL (distributed column passes over few local
+// columns) and the B381_NTT_GENERIC=1 cross-check of the specialised kernels.
+__global__ void __launch_bounds__(256, 2) k_ntt_generic(const __grid_constant__ ntt_pass_params p, const fr_t* in, fr_t* out) {
+  extern __shared__ uint4 smem[];
+  const uint32_t tile = 1u << (p.S + p.g + p.x);
+  const ntt_tile t{smem, smem + tile};
+  const uint64_t tile_id = p.tile_rot ? (blockIdx.x + p.tile_rot) % gridDim.x : blockIdx.x;
+  const ntt_tile_ctx c = ntt_tile_begin(p, tile_id, p.S, p.g, p.x, p.lo);
+  for (uint32_t pos = threadIdx.x; pos < tile; pos += blockDim.x) ntt_tile_load(p, c, pos, in, t);
+  __syncthreads();
+  const uint32_t steps = ntt_pass_steps(p.S);
+  const bool last_is_unit = p.lo == 0 && p.dist_shift == 0;
+  for (uint32_t step = 0; step < steps; step++) {
+    uint32_t rl, s;
+    ntt_pass_step(p.S, step, &rl, &s);
+    if (rl == 1) {
+      for (uint32_t q = threadIdx.x; q < tile / 2; q += blockDim.x) ntt_step_r2(p, c, q, s, t);
+    } else if (last_is_unit && s == 0) {
+      for (uint32_t q = threadIdx.x; q < tile / 4; q += blockDim.x) ntt_step_r4<true>(p, c, q, s, t);
+    } else {
+      for (uint32_t q = threadIdx.x; q < tile / 4; q += blockDim.x) ntt_step_r4<false>(p, c, q, s, t);
+    }
+    __syncthreads();
+  }
+  for (uint32_t pos = threadIdx.x; pos < tile; pos += blockDim.x) ntt_tile_store(p, c, pos, out, t);
 }
-static void launch_ntt_pass(const ntt_pass_params& p, const fr_t* in, fr_t* out, unsigned tiles, size_t smem, cudaStream_t st) {
-  const int r = ntt_rmax();
-  if (r == 3) {
-    cudaFuncSetAttribute(k_ntt_pass<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(uint4) * kTile);
-    k_ntt_pass<3><<<tiles, kNttThreads, smem, st>>>(p, in, out);
-  } else if (r == 2) {
-    cudaFuncSetAttribute(k_ntt_pass<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(uint4) * kTile);
-    k_ntt_pass<2><<<tiles, kNttThreads, smem, st>>>(p, in, out);
+
+// launch shape of the specialised kernels: threads per CTA / CTAs per SM (B381_NTT_SHAPE = 0..3 selects for A/B runs)
+struct ntt_shape { int nt, minb; };
+static int ntt_shape_id() {
+  static const int v = [] { const char* e = getenv("B381_NTT_SHAPE"); int x = e ? atoi(e) : 0; return x < 0 || x > 3 ? 0 : x; }();
+  return v;
+}
+static bool ntt_force_generic() {
+  static const bool v = [] { const char* e = getenv("B381_NTT_GENERIC"); return e && e[0] == '1'; }();
+  return v;
+}
+
+template <int S, bool LO0, int NT, int MINB>
+static void launch_k(const ntt_pass_params& p, const fr_t* in, fr_t* out, unsigned tiles, cudaStream_t st) {
+  constexpr size_t smem = 2 * sizeof(uint4) * kTile;
+  static bool attr_done = false;       // per instantiation
+  if (!attr_done) {
+    cudaFuncSetAttribute(k_ntt<S, LO0, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    attr_done = true;
+  }
+  k_ntt<S, LO0, NT, MINB><<<tiles, NT, smem, st>>>(p, in, out);
+}
+template <int S, bool LO0>
+static void launch_shape(const ntt_pass_params& p, const fr_t* in, fr_t* out, unsigned tiles, cudaStream_t st) {
+  switch (ntt_shape_id()) {
+    case 1: launch_k<S, LO0, 256, 2>(p, in, out, tiles, st); break;
+    case 2: launch_k<S, LO0, 512, 1>(p, in, out, tiles, st); break;
+    case 3: launch_k<S, LO0, 128, 3>(p, in, out, tiles, st); break;
+    default: launch_k<S, LO0, 256, 3>(p, in, out, tiles, st); break;
+  }
+}
+template <bool LO0, int S>
+static void launch_s(uint32_t Sr, const ntt_pass_params& p, const fr_t* in, fr_t* out, unsigned tiles, cudaStream_t st) {
+  if constexpr (S == 0) {
+    (void)Sr; (void)p; (void)in; (void)out; (void)tiles; (void)st;
   } else {
-    cudaFuncSetAttribute(k_ntt_pass<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * sizeof(uint4) * kTile);
-    k_ntt_pass<1><<<tiles, kNttThreads, smem, st>>>(p, in, out);
+    if (Sr == (uint32_t)S) launch_shape<S, LO0>(p, in, out, tiles, st);
+    else launch_s<LO0, S - 1>(Sr, p, in, out, tiles, st);
+  }
+}
+
+static void launch_ntt_pass(const ntt_pass_params& p, const fr_t* in, fr_t* out, unsigned tiles, cudaStream_t st) {
+  const uint32_t tile_log = p.S + p.g + p.x;
+  const bool full = tile_log == kNttTileLog && !ntt_force_generic();
+  if (full && p.lo == 0 && p.dist_shift == 0 && p.g == 0 && p.S >= 1 && p.S <= kNttTileLog) {
+    launch_s<true, (int)kNttTileLog>(p.S, p, in, out, tiles, st);
+  } else if (full && p.lo > 0 && p.x == 0 && p.S >= 1 && p.S <= kNttTileLog - 2) {
+    launch_s<false, (int)kNttTileLog - 2>(p.S, p, in, out, tiles, st);
+  } else {
+    const size_t smem = (size_t)2 * sizeof(uint4) << tile_log;
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(k_ntt_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(2 * sizeof(uint4) * kTile));
+      attr_done = true;
+    }
+    k_ntt_generic<<<tiles, 256, smem, st>>>(p, in, out);
   }
 }
 
@@ -78,6 +154,12 @@ __global__ void k_twiddle_subsample(const fr_t* top, uint32_t K, fr_t* table) {
   uint32_t k = 63 - __clzll(idx + 1);
   uint64_t j = idx + 1 - (1ull << k);
   table[idx] = top[j << (K - 1 - k)];
+}
+
+// inverse stage-major table from the forward one (ntt_core.cuh ntt_inverse_twiddle)
+__global__ void k_twiddle_inverse(const fr_t* fwd, uint64_t entries, fr_t* inv_table) {
+  uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx < entries) ntt_inverse_twiddle(idx, fwd, inv_table);
 }
 
 // single-thread setup: decide whether `root` is standard or Montgomery, find its order, n^-1 table
@@ -113,7 +195,8 @@ struct Domain {
   int device = -1;
   uint32_t K = 0;            // log2 of the root's order
   fr_t root_mont;            // primitive 2^K-th root, Montgomery
-  fr_t* table = nullptr;     // 2^K - 1 twiddles, stage-major
+  fr_t* table = nullptr;     // 2^K - 1 twiddles, stage-major; followed by the same for omega^-1
+  fr_t* inv_table = nullptr;
   fr_t ninv[33];             // 2^-k, Montgomery
   std::vector<CosetTable> cosets;
 };
@@ -131,7 +214,6 @@ static Domain& cur_domain() {
   d.device = dev;
   return d;
 }
-#define g_dom (cur_domain())
 
 static void release_locked() {
   Domain& d = cur_domain();
@@ -144,6 +226,7 @@ static void release_locked() {
 
 static int init_domain(const fr_t& root, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_dom_mu);
+  Domain& g_dom = cur_domain();
   if (g_dom.ready) return B381_SUCCESS;   // ICICLE semantics: repeated init is a no-op until release
   domain_probe* d_probe;
   domain_probe h;
@@ -157,19 +240,21 @@ static int init_domain(const fr_t& root, cudaStream_t st) {
   const uint32_t K = (uint32_t)h.log_order;
   fr_t* table;
   const uint64_t entries = (1ull << K) - 1;
-  if (cudaMalloc(&table, entries * sizeof(fr_t)) != cudaSuccess) return B381_OUT_OF_MEMORY;
+  if (cudaMalloc(&table, 2 * entries * sizeof(fr_t)) != cudaSuccess) return B381_OUT_OF_MEMORY;
   // top level: T[2^(K-1)-1 + j] = root^j, j < 2^(K-1)
   fr_t* top = table + ((1ull << (K - 1)) - 1);
   const uint64_t half = 1ull << (K - 1);
   fr_t one_m = {FR_ONE_INIT};
   k_fr_powers<<<grid_for((half + 63) / 64, 128), 128, 0, st>>>(h.root_mont, one_m, half, top);
   if (K > 1) k_twiddle_subsample<<<grid_for(half - 1, 256), 256, 0, st>>>(top, K, table);
+  k_twiddle_inverse<<<grid_for(entries, 256), 256, 0, st>>>(table, entries, table + entries);
   e = cudaStreamSynchronize(st);
   if (e == cudaSuccess) e = cudaGetLastError();
   if (e != cudaSuccess) { cudaFree(table); return map_cuda_error(e); }
   g_dom.K = K;
   g_dom.root_mont = h.root_mont;
   g_dom.table = table;
+  g_dom.inv_table = table + entries;
   memcpy(g_dom.ninv, h.ninv, sizeof(h.ninv));
   g_dom.ready = true;
   return B381_SUCCESS;
@@ -185,7 +270,7 @@ __global__ void k_fr_inv1(fr_t x, fr_t* out) {
 // Coset power tables, cached per (generator, log size, direction) -- the reference caches only the
 // first generator it sees (ntt_kernels.cu:1701-1705).  forward: g^i ; inverse: g^-k * 2^-n.
 // Caller holds g_dom_mu.
-static int coset_table(const fr_t& gen, uint32_t n, bool inverse, cudaStream_t st, const fr_t** out) {
+static int coset_table(Domain& g_dom, const fr_t& gen, uint32_t n, bool inverse, cudaStream_t st, const fr_t** out) {
   for (auto& c : g_dom.cosets)
     if (c.n == n && c.inverse == inverse && fr_host_eq(c.gen, gen)) { *out = c.dev; return B381_SUCCESS; }
   if (g_dom.cosets.size() >= 8) {          // small FIFO cache; eviction is rare, so a full sync is fine
@@ -231,15 +316,16 @@ static int ntt_run(const fr_t* input, int size, int dir, const b381_ntt_config* 
   cudaStream_t st = (cudaStream_t)cfg->stream;
 
   std::unique_lock<std::mutex> lk(g_dom_mu);
+  Domain& g_dom = cur_domain();
   if (!g_dom.ready || n > g_dom.K) return B381_INVALID_ARGUMENT;   // domain missing / too small (:724-731)
-  const fr_t* tw = g_dom.table;
+  const fr_t* tw = inverse ? g_dom.inv_table : g_dom.table;
   fr_t ninv = g_dom.ninv[n];
   const fr_t one_m = {FR_ONE_INIT};
   const fr_t* gen = reinterpret_cast<const fr_t*>(&cfg->coset_gen);
   bool has_coset = !fr_host_eq(*gen, one_m) && !fr_host_is_zero(*gen);
   const fr_t* ctab = nullptr;
   if (has_coset) {
-    int rc = coset_table(*gen, n, inverse, st, &ctab);
+    int rc = coset_table(g_dom, *gen, n, inverse, st, &ctab);
     if (rc != B381_SUCCESS) return rc;
   }
 
@@ -274,7 +360,6 @@ static int ntt_run(const fr_t* input, int size, int dir, const b381_ntt_config* 
       p.total = total;
       if (cfg->columns_batch) { p.estride = batch; p.bstride = 1; }
       else { p.estride = 1; p.bstride = 1ull << n; }
-      p.inverse = inverse;
       p.twiddles = tw;
       const bool first = (i == 0), last = (i + 1 == P);
       p.perm_in = first && perm_in;
@@ -288,8 +373,7 @@ static int ntt_run(const fr_t* input, int size, int dir, const b381_ntt_config* 
       fr_t* dst = last ? d_out : work;
       const uint32_t tile_log = p.S + p.g + p.x;
       const uint64_t tiles = (total + (1ull << tile_log) - 1) >> tile_log;
-      const size_t smem = (size_t)2 * sizeof(uint4) << tile_log;
-      launch_ntt_pass(p, src, dst, (unsigned)tiles, smem, st);
+      launch_ntt_pass(p, src, dst, (unsigned)tiles, st);
     }
     g_ntt_last_info[0] = (int)P; g_ntt_last_info[1] = (int)n; g_ntt_last_info[2] = (int)batch;
     lk.unlock();   // tables stay valid: release_domain synchronises the device before freeing
@@ -315,26 +399,14 @@ static int ntt_dist_columns(fr_t* data, uint32_t log_n, uint32_t log_gpus, uint3
   const uint32_t lo = log_n - a;            // global bit where the column index ends
   if (lo < log_gpus + 2) return B381_INVALID_ARGUMENT;   // keep >= 4 adjacent elements per tile row
   if (peer_rows && log_gpus > 3) return B381_INVALID_ARGUMENT;   // ntt_pass_params::peer_out holds 8 GPUs
-  const uint32_t logL = lo - log_gpus;
-  const uint32_t n_loc = log_n - log_gpus;
   std::unique_lock<std::mutex> lk(g_dom_mu);
+  Domain& g_dom = cur_domain();
   if (!g_dom.ready || log_n > g_dom.K) return B381_INVALID_ARGUMENT;
-  const fr_t* tw = g_dom.table;
-  // split the `a` upper stages into passes of <= 9 stages with g = min(tile - S, logL) adjacent columns
-  uint32_t rest = a, np = (a + 8) / 9, hi = n_loc;
-  for (uint32_t i = 0; i < np; i++) {
-    uint32_t S = (rest + (np - i) - 1) / (np - i);
-    ntt_pass_params p;
-    memset(&p, 0, sizeof(p));
-    p.n = n_loc; p.lo = hi - S; p.S = S;
-    p.g = kNttTileLog - S;
-    if (p.g > logL) p.g = logL;
-    if (p.g > p.lo) p.g = p.lo;
-    p.total = 1ull << n_loc;
-    p.estride = 1; p.bstride = 1ull << n_loc;
-    p.inverse = dir == B381_NTT_INVERSE;
-    p.twiddles = tw;
-    p.dist_shift = log_gpus; p.dist_logL = logL; p.dist_lo = lo; p.dist_lbase = rank << logL;
+  const fr_t* tw = dir == B381_NTT_INVERSE ? g_dom.inv_table : g_dom.table;
+  ntt_pass_params passes[8];
+  const int np = ntt_dist_passes(log_n, log_gpus, rank, a, tw, passes);
+  for (int i = 0; i < np; i++) {
+    ntt_pass_params& p = passes[i];
     if (peer_rows && i + 1 == np) {
       p.peer_on = 1;
       p.peer_logR = a - log_gpus;
@@ -346,9 +418,7 @@ static int ntt_dist_columns(fr_t* data, uint32_t log_n, uint32_t log_gpus, uint3
     const uint32_t tile_log = p.S + p.g;
     const uint64_t tiles = p.total >> tile_log;
     if (p.peer_on) p.tile_rot = (uint32_t)((tiles >> log_gpus) * rank);   // tiles are ordered by destination GPU
-    launch_ntt_pass(p, data, data, (unsigned)tiles, (size_t)2 * sizeof(uint4) << tile_log, st);
-    hi -= S;
-    rest -= S;
+    launch_ntt_pass(p, data, data, (unsigned)tiles, st);
   }
   lk.unlock();
   return map_cuda_error(cudaGetLastError());
@@ -387,6 +457,7 @@ int b381_ntt(const b381_fr* in, int size, int dir, const b381_ntt_config* cfg, b
 int b381_ntt_get_rou_from_domain(uint64_t logn, b381_fr* rou) {
   if (!rou) return B381_INVALID_POINTER;
   std::lock_guard<std::mutex> lk(g_dom_mu);
+  Domain& g_dom = cur_domain();
   if (!g_dom.ready || logn > g_dom.K) return B381_INVALID_ARGUMENT;
   fr_t v;
   if (logn == 0) {

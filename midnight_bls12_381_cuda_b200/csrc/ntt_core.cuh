@@ -1,15 +1,19 @@
-// Per-thread bodies of the Fr NTT (tile load / butterfly stage / tile store), shared by the CUDA
-// kernel in ntt.cu and the CPU-only harness tests/host/ntt_host_sim.cpp.
+// Per-thread bodies of the Fr NTT (tile load / register-blocked butterfly steps / tile store) and the host-side pass
+// planner, shared by the CUDA kernels in ntt.cu and the CPU-only harness tests/host/ntt_host_sim.cpp.
 //
 // Algorithm (ours; the reference's is bls12-381/src/field/ntt_kernels.cu:110-958):
-//   * decimation-in-frequency radix-2 over log2(N) stages, grouped into PASSES of up to 11 stages;
-//     a pass keeps a 2048-element tile (64 KB) in shared memory, so N = 2^24 costs 3 trips through
-//     HBM instead of the reference's 12 radix-4 passes + bit-reversal pass + D2D copy (:772-810).
+//   * decimation-in-frequency radix-2 over log2(N) stages, grouped into PASSES of S stages; a pass keeps a
+//     2^TL-element tile in shared memory (TL = 11: 64 KB), so N = 2^24 is 3 trips through HBM (8 + 8 + 8 stages)
+//     instead of the reference's 12 radix-4 passes + bit-reversal pass + D2D copy (:772-810).
 //   * stage k butterfly on (i, i+2^k):  (a, b) -> (a+b, (a-b) * w),  w = omega_{2^(k+1)}^(i mod 2^k).
-//     Twiddles come from ONE stage-major table  T[2^k - 1 + j] = omega_{2^(k+1)}^j  (j < 2^k) that
-//     serves every transform size of the domain (the reference keeps a full-length table per log
-//     size, ~2 GiB for max-log 24: ntt_kernels.cu:1607-1679).  Inverse twiddles are read from the
-//     same table:  w^-j = -T[2^k - j].
+//     Inside a pass two stages are run at a time on FOUR tile slots held in registers (a radix-4 step: 4 butterflies,
+//     3 distinct twiddles, one trip smem -> registers -> smem per two stages); the step is straight-line code -- no
+//     data- or parameter-dependent branch between the loads and the stores -- so the two independent Montgomery
+//     products of every stage interleave.  An odd S starts with one plain radix-2 step.
+//   * Twiddles come from stage-major tables  T[2^k - 1 + j] = omega_{2^(k+1)}^j  (j < 2^k), one for omega and one for
+//     omega^-1 (the inverse transform is the same code with the other table), which serve every transform size of the
+//     domain (the reference keeps a full-length table per log size, ~2 GiB for max-log 24: ntt_kernels.cu:1607-1679).
+//     In the last pass the final step (stages 1 and 0) needs one product per four elements: T_0[0] = T_1[0] = 1.
 //   * DIF leaves y[bitrev(i)] at position i, so ordering is a pure addressing choice:
 //     load position i from in[perm_in(i)], store position i to out[perm_out(i)]
 //       kNN: in i      / out rev(i)        kNR: in i      / out i
@@ -19,6 +23,8 @@
 //   * coset (x[i]*g^i before a forward NTT, y[k]*g^-k after an inverse one; include/ntt.cuh:123-183)
 //     and the 1/N of the inverse are fused into the first pass's load / last pass's store.
 #pragma once
+#include <cstring>
+
 #include "field.cuh"
 
 namespace b381 {
@@ -27,15 +33,14 @@ struct ntt_pass_params {
   uint32_t n;          // log2 of the transform length
   uint32_t lo;         // this pass runs stages k = lo+S-1 ... lo
   uint32_t S;          // stages in this pass
-  uint32_t g;          // log2 of adjacent low-index elements kept together in a tile (coalescing)
-  uint32_t x;          // lo == 0 only: log2 of whole sub-transforms packed into one tile (small N)
+  uint32_t g;          // log2 of adjacent low-index elements kept together in a tile (coalescing); tile = 2^(S+g+x)
+  uint32_t x;          // lo == 0 only: log2 of whole 2^S-blocks packed into one tile
   uint64_t total;      // batch * N elements
   uint64_t estride;    // address = batch_index * bstride + i * estride
   uint64_t bstride;
-  uint32_t inverse;    // use conjugate twiddles
   uint32_t perm_in;    // gather input from bit-reversed index (first pass only)
   uint32_t perm_out;   // scatter output to bit-reversed index (last pass only)
-  const fr_t* twiddles;   // stage-major table
+  const fr_t* twiddles;   // stage-major table of omega (forward) or omega^-1 (inverse)
   const fr_t* pre_scale;  // optional: multiply position i by pre_scale[i] on load  (coset, forward)
   const fr_t* post_scale; // optional: multiply logical output k by post_scale[k] on store (coset, inverse)
   fr_t post_const;        // used when has_post_const: multiply every output (1/N)
@@ -58,13 +63,6 @@ struct ntt_pass_params {
   fr_t* peer_out[8];      // row buffer of every GPU, mapped into this process (CUDA IPC)
 };
 
-// local flat index -> global flat index (identity when not distributed)
-B381_DI uint64_t ntt_global_index(const ntt_pass_params& p, uint64_t J) {
-  if (p.dist_shift == 0) return J;
-  uint64_t hi = J >> p.dist_logL, l = J & ((1ull << p.dist_logL) - 1);
-  return (hi << p.dist_lo) | (p.dist_lbase + l);
-}
-
 B381_HD uint32_t bitrev32(uint32_t v, uint32_t bits) {
 #if defined(__CUDA_ARCH__)
   return bits ? (__brev(v) >> (32 - bits)) : 0;
@@ -77,9 +75,8 @@ B381_HD uint32_t bitrev32(uint32_t v, uint32_t bits) {
 
 // shared-memory tile: element e lives as two 16-byte halves in separate arrays so that a warp
 // touching consecutive elements hits all 32 banks exactly once per 8 lanes.  Slot `pos` is stored at
-// pos ^ ((pos >> 3) & 7): a quarter-warp whose lanes step by 8 slots (the radix-8 step over the three
-// lowest slot bits, one register group per lane) then still spreads over all eight 16-byte bank groups,
-// and lanes on consecutive slots keep doing so (the XOR term is the same for all eight).
+// pos ^ ((pos >> 3) & 7): a quarter-warp whose lanes step by 8 slots then still spreads over all eight 16-byte bank
+// groups, and lanes on consecutive slots keep doing so (the XOR term is the same for all eight).
 struct ntt_tile {
   uint4* lo;
   uint4* hi;
@@ -149,16 +146,42 @@ B381_DI void fr_gstore(fr_t* p, const fr_t& v) {
 #endif
 }
 
-// Flat index of tile slot `pos` (pos = m*G + l') of tile `tile_id`:
-//   I = (H << hi) | (m << lo) | (l0 + l'),  hi = lo+S,  tiles enumerate (H, l0/G) with l0 fastest.
-B381_DI uint64_t ntt_tile_index(const ntt_pass_params& p, uint64_t tile_id, uint32_t pos) {
-  if (p.lo == 0) return (tile_id << (p.S + p.x)) | pos;   // contiguous tile (g == 0)
-  const uint32_t G = 1u << p.g;
-  const uint32_t groups_lo = (1u << p.lo) >> p.g;   // number of l0 groups (lo >= g by construction)
-  uint64_t H = tile_id / groups_lo;
-  uint32_t l0 = (uint32_t)(tile_id % groups_lo) << p.g;
-  uint32_t m = pos >> p.g, lp = pos & (G - 1);
-  return (H << (p.lo + p.S)) | ((uint64_t)m << p.lo) | (l0 + lp);
+// ---- what a CTA knows about its tile, computed once (uniform across the CTA) --------------------------------
+// Flat index of tile slot `pos` = (m << g) | l'  (m: the S + x bits the pass works on, l': g adjacent low bits):
+//   I = base + (m << lo) + l',   base = (H << (lo + S)) | l0   with tiles enumerating (H, l0 >> g), l0 fastest.
+// (lo == 0 has g == 0 and I = (tile << (S + x)) | pos, the same formula with base = tile << (S + x).)
+// The pass shape (S, g, x, lo) travels in here rather than being read from the parameter block, so that a kernel
+// specialised on the shape hands the steps compile-time constants.
+struct ntt_tile_ctx {
+  uint32_t S, g, x, lo; // shape of the pass (see ntt_pass_params)
+  uint64_t base;        // flat index of slot 0
+  uint32_t lglob;       // GLOBAL low index part of slot 0's column l0 (== l0 when not distributed)
+  uint32_t jshift;      // bit position of m in the GLOBAL index: lo (+ dist_shift)
+};
+B381_DI ntt_tile_ctx ntt_tile_begin(const ntt_pass_params& p, uint64_t tile_id, uint32_t S, uint32_t g, uint32_t x, uint32_t lo) {
+  ntt_tile_ctx c;
+  c.S = S; c.g = g; c.x = x; c.lo = lo;
+  uint32_t l0 = 0;
+  if (lo == 0) {
+    c.base = tile_id << (S + x);
+  } else {
+    const uint32_t glog = lo - g;                         // log2 of l0 groups per H (lo >= g by construction)
+    const uint64_t H = tile_id >> glog;
+    l0 = (uint32_t)(tile_id & ((1ull << glog) - 1)) << g;
+    c.base = (H << (lo + S)) | l0;
+  }
+  c.jshift = lo + (lo ? p.dist_shift : 0u);           // distributed passes never have lo == 0
+  c.lglob = l0;
+  if (p.dist_shift) {
+    // local low part l0 spans column bits [0, logL) and row bits [logL, lo): the rows move up by dist_shift and the
+    // column gets this GPU's first column added.  Slots add l' < 2^g <= 2^logL to the column part only.
+    const uint32_t col = l0 & ((1u << p.dist_logL) - 1), row = l0 >> p.dist_logL;
+    c.lglob = (row << p.dist_lo) | (p.dist_lbase + col);
+  }
+  return c;
+}
+B381_DI uint64_t ntt_slot_index(const ntt_tile_ctx& c, uint32_t pos) {
+  return c.base + ((uint64_t)(pos >> c.g) << c.lo) + (pos & ((1u << c.g) - 1));
 }
 
 B381_DI uint64_t ntt_addr(const ntt_pass_params& p, uint64_t I, bool permute) {
@@ -169,83 +192,80 @@ B381_DI uint64_t ntt_addr(const ntt_pass_params& p, uint64_t I, bool permute) {
 }
 
 // phase 1: slot `pos` <- global
-B381_DI void ntt_tile_load(const ntt_pass_params& p, uint64_t tile_id, uint32_t pos, const fr_t* in, const ntt_tile& t) {
-  uint64_t I = ntt_tile_index(p, tile_id, pos);
+B381_DI void ntt_tile_load(const ntt_pass_params& p, const ntt_tile_ctx& c, uint32_t pos, const fr_t* in, const ntt_tile& t) {
+  uint64_t I = ntt_slot_index(c, pos);
   if (I >= p.total) return;
   fr_t v = fr_gload(in + ntt_addr(p, I, p.perm_in != 0));
   if (p.pre_scale) v = mul(v, fr_gload_ro(p.pre_scale + (I & ((1ull << p.n) - 1))));
   tile_put(t, pos, v);
 }
 
-// phase 2: butterfly q of in-pass stage s (global stage k = lo + s)
-B381_DI void ntt_tile_stage(const ntt_pass_params& p, uint64_t tile_id, uint32_t q, uint32_t s, const ntt_tile& t) {
-  const uint32_t bit = s + p.g;                       // slot bit that separates the pair
-  uint32_t pos0 = ((q >> bit) << (bit + 1)) | (q & ((1u << bit) - 1));
-  uint32_t pos1 = pos0 | (1u << bit);
-  uint64_t I0 = ntt_tile_index(p, tile_id, pos0);
-  if (I0 >= p.total) return;
-  const uint32_t k = p.lo + s + p.dist_shift;         // global stage
-  uint32_t j = (uint32_t)(ntt_global_index(p, I0) & ((1ull << k) - 1));    // i mod 2^k
+// (a, b) -> (a + b, (a - b) * w)
+B381_DI void ntt_bfly(fr_t& a, fr_t& b, const fr_t& w) {
+  const fr_t d = sub(a, b);
+  a = add(a, b);
+  b = mul(d, w);
+}
+B381_DI void ntt_bfly_unit(fr_t& a, fr_t& b) {   // twiddle 1
+  const fr_t d = sub(a, b);
+  a = add(a, b);
+  b = d;
+}
+
+// twiddle index of the group whose first slot is `base_pos` (slot bits [bit0, bit0 + R) clear), in-pass stage s:
+//   j0 = ((m mod 2^s) << jshift) + lglob + l'       (the GLOBAL index of the slot, modulo 2^(jshift + s))
+B381_DI uint32_t ntt_twiddle_j0(const ntt_tile_ctx& c, uint32_t base_pos, uint32_t s) {
+  const uint32_t m = base_pos >> c.g, lp = base_pos & ((1u << c.g) - 1);
+  return ((m & ((1u << s) - 1)) << c.jshift) + c.lglob + lp;
+}
+
+// phase 2a: one radix-2 step (in-pass stage s) on group q of the tile's 2^(TL-1) pairs
+B381_DI void ntt_step_r2(const ntt_pass_params& p, const ntt_tile_ctx& c, uint32_t q, uint32_t s, const ntt_tile& t) {
+  const uint32_t bit0 = s + c.g;
+  const uint32_t pos0 = ((q >> bit0) << (bit0 + 1)) | (q & ((1u << bit0) - 1)), pos1 = pos0 | (1u << bit0);
+  const uint32_t k = c.jshift + s;
+  const fr_t w = fr_gload_ro(p.twiddles + ((1ull << k) - 1) + ntt_twiddle_j0(c, pos0, s));
   fr_t a = tile_get(t, pos0), b = tile_get(t, pos1);
-  fr_t sum = add(a, b);
-  fr_t d, w;
-  const fr_t* T = p.twiddles + ((1ull << k) - 1);
-  if (!p.inverse || j == 0) {
-    d = sub(a, b);
-    w = fr_gload_ro(T + j);
-  } else {                                            // w^-j = -T[2^k - j]
-    d = sub(b, a);
-    w = fr_gload_ro(T + ((1u << k) - j));
-  }
-  tile_put(t, pos0, sum);
-  tile_put(t, pos1, (k == 0) ? d : mul(d, w));        // stage 0 twiddle is 1
+  ntt_bfly(a, b, w);
+  tile_put(t, pos0, a);
+  tile_put(t, pos1, b);
 }
 
-// One butterfly on registers, global stage k = lo + s (+ dist_shift), first element at tile slot pos0.
-B381_DI void ntt_bfly(const ntt_pass_params& p, uint64_t tile_id, uint32_t pos0, uint32_t s, fr_t& a, fr_t& b) {
-  const uint32_t k = p.lo + s + p.dist_shift;
-  const uint64_t I0 = ntt_tile_index(p, tile_id, pos0);
-  const uint32_t j = (uint32_t)(ntt_global_index(p, I0) & ((1ull << k) - 1));
-  const fr_t sum = add(a, b);
-  fr_t d, w;
-  const fr_t* T = p.twiddles + ((1ull << k) - 1);
-  if (!p.inverse || j == 0) {
-    d = sub(a, b);
-    w = fr_gload_ro(T + j);
-  } else {
-    d = sub(b, a);
-    w = fr_gload_ro(T + ((1u << k) - j));
+// phase 2b: one radix-4 step = in-pass stages s+1 and s on group q of the tile's 2^(TL-2) quadruples: slots
+// base | a << bit0, a = 0..3.  Stage s+1 pairs (0,2) and (1,3) with twiddles T_{k+1}[j0] and T_{k+1}[j0 + 2^k]; stage s
+// pairs (0,1) and (2,3), both with T_k[j0]  (k = jshift + s: global stage of in-pass stage s).
+// LAST = the pass's lo is 0 and s == 0: T_0[0] = T_1[0] = 1, only T_1[1] = omega_4 is a real product.
+template <bool LAST>
+B381_DI void ntt_step_r4(const ntt_pass_params& p, const ntt_tile_ctx& c, uint32_t q, uint32_t s, const ntt_tile& t) {
+  const uint32_t bit0 = s + c.g;
+  const uint32_t base = ((q >> bit0) << (bit0 + 2)) | (q & ((1u << bit0) - 1));
+  const uint32_t p1 = base | (1u << bit0), p2 = base | (2u << bit0), p3 = base | (3u << bit0);
+  if (LAST) {
+    const fr_t w4 = fr_gload_ro(p.twiddles + 2);          // T_1[1] = omega_4 (or its inverse)
+    fr_t x0 = tile_get(t, base), x1 = tile_get(t, p1), x2 = tile_get(t, p2), x3 = tile_get(t, p3);
+    ntt_bfly_unit(x0, x2);
+    ntt_bfly(x1, x3, w4);
+    ntt_bfly_unit(x0, x1);
+    ntt_bfly_unit(x2, x3);
+    tile_put(t, base, x0); tile_put(t, p1, x1); tile_put(t, p2, x2); tile_put(t, p3, x3);
+    return;
   }
-  a = sum;
-  b = (k == 0) ? d : mul(d, w);
-}
-
-// phase 2, register-blocked: R consecutive in-pass stages s0+R-1 .. s0 on the 2^R tile slots that differ
-// in slot bits [s0+g, s0+g+R) -- 2^R elements travel smem -> registers -> smem once for R stages
-// (R * 2^(R-1) butterflies), instead of once per stage.  Group q of the tile's 2^(S+g+x-R) groups.
-template <int R>
-B381_DI void ntt_tile_stages(const ntt_pass_params& p, uint64_t tile_id, uint32_t q, uint32_t s0, const ntt_tile& t) {
-  const uint32_t bit0 = s0 + p.g;
-  const uint32_t base = ((q >> bit0) << (bit0 + R)) | (q & ((1u << bit0) - 1));
-  if (ntt_tile_index(p, tile_id, base) >= p.total) return;   // a group never straddles two transforms
-  fr_t v[1 << R];
-#pragma unroll
-  for (int a = 0; a < (1 << R); a++) v[a] = tile_get(t, base | ((uint32_t)a << bit0));
-#pragma unroll
-  for (int r = R - 1; r >= 0; r--) {
-#pragma unroll
-    for (int a = 0; a < (1 << R); a++) {
-      if (a & (1 << r)) continue;
-      ntt_bfly(p, tile_id, base | ((uint32_t)a << bit0), s0 + (uint32_t)r, v[a], v[a | (1 << r)]);
-    }
-  }
-#pragma unroll
-  for (int a = 0; a < (1 << R); a++) tile_put(t, base | ((uint32_t)a << bit0), v[a]);
+  const uint32_t k = c.jshift + s;
+  const uint32_t j0 = ntt_twiddle_j0(c, base, s);
+  const fr_t* Tk = p.twiddles + ((1ull << k) - 1) + j0;
+  const fr_t* Tk1 = p.twiddles + ((2ull << k) - 1) + j0;
+  const fr_t wa = fr_gload_ro(Tk1), wb = fr_gload_ro(Tk1 + (1ull << k)), wl = fr_gload_ro(Tk);
+  fr_t x0 = tile_get(t, base), x1 = tile_get(t, p1), x2 = tile_get(t, p2), x3 = tile_get(t, p3);
+  ntt_bfly(x0, x2, wa);
+  ntt_bfly(x1, x3, wb);
+  ntt_bfly(x0, x1, wl);
+  ntt_bfly(x2, x3, wl);
+  tile_put(t, base, x0); tile_put(t, p1, x1); tile_put(t, p2, x2); tile_put(t, p3, x3);
 }
 
 // phase 3: slot `pos` -> global
-B381_DI void ntt_tile_store(const ntt_pass_params& p, uint64_t tile_id, uint32_t pos, fr_t* out, const ntt_tile& t) {
-  uint64_t I = ntt_tile_index(p, tile_id, pos);
+B381_DI void ntt_tile_store(const ntt_pass_params& p, const ntt_tile_ctx& c, uint32_t pos, fr_t* out, const ntt_tile& t) {
+  uint64_t I = ntt_slot_index(c, pos);
   if (I >= p.total) return;
   fr_t v = tile_get(t, pos);
   if (p.post_scale) {
@@ -265,6 +285,25 @@ B381_DI void ntt_tile_store(const ntt_pass_params& p, uint64_t tile_id, uint32_t
   fr_gstore(out + ntt_addr(p, I, p.perm_out != 0), v);
 }
 
+// The whole pass as seen by thread `tid` of `nthreads`, with `sync()` the CTA barrier: exactly what the CUDA kernel
+// runs (ntt.cu) and what the host harness replays thread by thread, phase by phase.
+// TL = log2 of the tile; S = p.S is a template parameter so that every step's shifts and masks are constants.
+template <int TL>
+struct ntt_pass_shape {
+  static constexpr uint32_t tile = 1u << TL;
+};
+// phase list of a pass with S stages: optional radix-2 step at stage S-1 (S odd), then radix-4 steps down to stage 0.
+// step index -> (radix, s): used identically by the kernel's unrolled loop and by the host harness.
+B381_HD uint32_t ntt_pass_steps(uint32_t S) { return (S + 1) / 2; }
+B381_HD void ntt_pass_step(uint32_t S, uint32_t step, uint32_t* radix_log, uint32_t* s) {
+  if (S & 1) {
+    if (step == 0) { *radix_log = 1; *s = S - 1; return; }
+    *radix_log = 2; *s = S - 1 - 2 * step;
+  } else {
+    *radix_log = 2; *s = S - 2 - 2 * step;
+  }
+}
+
 // ---- domain / table generation bodies -------------------------------------------------------
 // out[j] = base * g^j for j in [chunk*len, chunk*len+len) : one pow + (len-1) multiplications.
 B381_DI void fr_powers_chunk(uint64_t chunk, uint32_t len, uint64_t count, const fr_t& g, const fr_t& base, fr_t* out) {
@@ -276,31 +315,82 @@ B381_DI void fr_powers_chunk(uint64_t chunk, uint32_t len, uint64_t count, const
     cur = mul(cur, g);
   }
 }
+// inverse table from the forward one: Tinv_k[j] = omega^-j = -T_k[2^k - j]  (j > 0),  Tinv_k[0] = 1
+B381_DI void ntt_inverse_twiddle(uint64_t idx, const fr_t* fwd, fr_t* inv_table) {
+  uint32_t k = 63;
+  while (!(((idx + 1) >> k) & 1)) k--;
+  const uint64_t j = idx + 1 - (1ull << k);
+  inv_table[idx] = j ? neg(fwd[(1ull << k) - 1 + ((1ull << k) - j)]) : fwd[idx];
+}
 
 // ---- pass planner (host) --------------------------------------------------------------------
 constexpr uint32_t kNttTileLog = 11;   // 2048 elements = 64 KB of shared memory per CTA
 struct ntt_pass_plan { uint32_t lo, S, g, x; };
 
-// Last pass: up to 11 stages on contiguous tiles.  Earlier passes: at most 9 stages each, so that a
-// tile row keeps >= 4 adjacent elements (128 B contiguous) for coalescing.
-// Fills `out` (capacity 8) and returns the number of passes.
-inline int ntt_plan_passes(uint32_t n, ntt_pass_plan* out) {
+// Splits the n stages into passes for a 2^tl-element tile.  The last pass (lo = 0) works on contiguous tiles and may
+// take up to tl stages; earlier passes take at most tl - 2, so that a tile row keeps >= 4 adjacent elements (128 B
+// contiguous) for coalescing.  Among the splits with the fewest passes, stage counts are balanced and EVEN where
+// possible (an odd count costs one extra radix-2 step = one more trip through shared memory): 24 -> 8 + 8 + 8,
+// 22 -> 6 + 8 + 8, 20 -> 9 + 11.  Fills `out` (capacity 8), highest stages first, and returns the number of passes.
+inline int ntt_plan_passes(uint32_t n, ntt_pass_plan* out, uint32_t tl = kNttTileLog) {
   int np = 0;
-  if (n <= kNttTileLog) {
-    out[np++] = ntt_pass_plan{0, n, 0, kNttTileLog - n};
+  if (n <= tl) {
+    out[np++] = ntt_pass_plan{0, n, 0, tl - n};
     return np;
   }
-  uint32_t rest = n - kNttTileLog;
-  uint32_t upper = (rest + 8) / 9;
+  const uint32_t up_max = tl - 2;
+  uint32_t P = 2;
+  while ((P - 1) * up_max + tl < n) P++;
+  uint32_t S[8];
+  // balanced start: every pass floor(n / P), remainder to the last passes; then make counts even by moving single
+  // stages between neighbours where the limits allow
+  for (uint32_t i = 0; i < P; i++) S[i] = n / P + ((i >= P - n % P) ? 1u : 0u);
+  auto ok = [&](uint32_t i, uint32_t v) { return v >= 1 && v <= (i + 1 == P ? tl : up_max); };
+  for (uint32_t i = 0; i + 1 < P; i++) {
+    if ((S[i] & 1) == 0) continue;
+    // find a later odd pass to pair with
+    for (uint32_t j = i + 1; j < P; j++) {
+      if (!(S[j] & 1)) continue;
+      if (ok(i, S[i] - 1) && ok(j, S[j] + 1)) { S[i]--; S[j]++; }
+      else if (ok(i, S[i] + 1) && ok(j, S[j] - 1)) { S[i]++; S[j]--; }
+      break;
+    }
+  }
   uint32_t hi = n;
-  for (uint32_t i = 0; i < upper; i++) {
-    uint32_t S = (rest + (upper - i) - 1) / (upper - i);
-    out[np++] = ntt_pass_plan{hi - S, S, kNttTileLog - S, 0};
+  for (uint32_t i = 0; i < P; i++) {
+    if (i + 1 < P) out[np++] = ntt_pass_plan{hi - S[i], S[i], tl - S[i], 0};
+    else out[np++] = ntt_pass_plan{0, S[i], 0, tl - S[i]};
+    hi -= S[i];
+  }
+  return np;
+}
+
+// Column passes of the distributed (four-step) transform: the top `a` DIF stages of a 2^log_n transform on rank's
+// column block (n_loc = log_n - log_gpus local index bits), split into passes of <= tl - 2 stages with
+// g = min(tl - S, logL, lo) adjacent columns.  Fills `out` (capacity 8) with everything but the peer pointers.
+inline int ntt_dist_passes(uint32_t log_n, uint32_t log_gpus, uint32_t rank, uint32_t a, const fr_t* tw,
+                           ntt_pass_params* out, uint32_t tl = kNttTileLog) {
+  const uint32_t lo_glob = log_n - a;           // global bit where the column index ends
+  const uint32_t logL = lo_glob - log_gpus, n_loc = log_n - log_gpus;
+  const uint32_t up_max = tl - 2;
+  uint32_t rest = a, np = (a + up_max - 1) / up_max, hi = n_loc;
+  for (uint32_t i = 0; i < np; i++) {
+    const uint32_t S = (rest + (np - i) - 1) / (np - i);
+    ntt_pass_params p;
+    memset(&p, 0, sizeof(p));
+    p.n = n_loc; p.lo = hi - S; p.S = S;
+    p.g = tl - S;
+    if (p.g > logL) p.g = logL;
+    if (p.g > p.lo) p.g = p.lo;
+    p.total = 1ull << n_loc;
+    p.estride = 1; p.bstride = 1ull << n_loc;
+    p.twiddles = tw;
+    p.dist_shift = log_gpus; p.dist_logL = logL; p.dist_lo = lo_glob; p.dist_lbase = rank << logL;
+    out[i] = p;
     hi -= S;
     rest -= S;
   }
-  out[np++] = ntt_pass_plan{0, kNttTileLog, 0, 0};
-  return np;
+  return (int)np;
 }
 
 }  // namespace b381

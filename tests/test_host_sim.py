@@ -131,7 +131,7 @@ def test_msm_pipeline_g2_and_precompute(sims):
 ORD = ["NN", "NR", "RN", "RR"]
 
 
-def run_ntt(sims, n, batch, inverse, ordering, columns, g, inplace, vecs):
+def run_ntt(sims, n, batch, inverse, ordering, columns, g, inplace, vecs, tile_log=11):
     N = 1 << n
     flat = [0] * (N * batch)
     for b in range(batch):
@@ -144,7 +144,7 @@ def run_ntt(sims, n, batch, inverse, ordering, columns, g, inplace, vecs):
         for v in flat:
             f.write(P.fr_bytes(P.fr_to_mont(v)))
     r = subprocess.run([sims["ntt_host_sim"], str(n), str(batch), str(int(inverse)), str(ordering), str(int(columns)),
-                        str(int(bool(g))), str(int(inplace)), path], capture_output=True, text=True, check=True)
+                        str(int(bool(g))), str(int(inplace)), path, str(tile_log)], capture_output=True, text=True, check=True)
     raw = bytes.fromhex(r.stdout.strip())
     flat = [P.fr_from_mont(int.from_bytes(raw[32 * i:32 * i + 32], "little")) for i in range(N * batch)]
     return [[flat[(i * batch + b) if columns else (b * N + i)] for i in range(N)] for b in range(batch)]
@@ -171,3 +171,41 @@ def test_ntt_passes(sims, n):
             got = run_ntt(sims, n, batch, inverse, ordering, columns, g, inplace, vecs)
             for b in range(batch):
                 assert got[b] == expect_ntt(vecs[b], inverse, ordering, g), (n, batch, columns, inverse, ordering, g, inplace)
+
+
+@pytest.mark.parametrize("n,tile_log", [(6, 4), (7, 4), (9, 4), (10, 5), (12, 5), (13, 6)])
+def test_ntt_multi_pass_plans(sims, n, tile_log):
+    """the 2-, 3- and 4-pass plans (what 2^12..2^29 use with the kernels' 2^11 tile) on small transforms: the harness
+    shrinks the tile, the planner and the per-thread bodies are the kernels' own."""
+    rng = P.SplitMix64(199 + n)
+    for batch, columns in ((1, False), (2, False), (2, True)):
+        vecs = [[rng.fr() for _ in range(1 << n)] for _ in range(batch)]
+        for inverse, ordering, g, inplace in ((False, 0, 0, True), (True, 0, 0, False), (False, 1, 7, True), (True, 2, 7, True),
+                                              (False, 3, 0, False)):
+            got = run_ntt(sims, n, batch, inverse, ordering, columns, g, inplace, vecs, tile_log)
+            for b in range(batch):
+                assert got[b] == expect_ntt(vecs[b], inverse, ordering, g), (n, tile_log, batch, columns, inverse, ordering, g)
+
+
+@pytest.mark.parametrize("n,log_gpus,a,tile_log", [(8, 1, 4, 11), (10, 2, 5, 11), (10, 3, 5, 4), (12, 1, 6, 5), (12, 3, 6, 5),
+                                                    (13, 2, 7, 5)])
+def test_ntt_distributed_columns(sims, n, log_gpus, a, tile_log):
+    """four-step transform with every rank emulated in turn (column passes with GLOBAL-index twiddles, exchange fused
+    into the last pass's stores or done as a transpose, row transforms): the concatenated row blocks are the
+    bit-reversed-order (kNR) transform of the whole vector, forward and inverse."""
+    rng = P.SplitMix64(299 + n)
+    vec = [rng.fr() for _ in range(1 << n)]
+    path = os.path.join(sims["dir"], f"ntt_dist_{n}.bin")
+    with open(path, "wb") as f:
+        f.write(P.fr_bytes(P.fr_to_mont(P.fr_omega(n))))
+        f.write(P.fr_bytes(P.fr_to_mont(1)))
+        for v in vec:
+            f.write(P.fr_bytes(P.fr_to_mont(v)))
+    for inverse in (False, True):
+        exp = P.apply_ordering(P.ntt(vec, inverse=inverse), "NR", "out")
+        for fused in (1, 0):
+            r = subprocess.run([sims["ntt_host_sim"], "dist", str(n), str(log_gpus), str(a), str(int(inverse)), str(fused), path,
+                                str(tile_log)], capture_output=True, text=True, check=True)
+            raw = bytes.fromhex(r.stdout.strip())
+            got = [P.fr_from_mont(int.from_bytes(raw[32 * i:32 * i + 32], "little")) for i in range(1 << n)]
+            assert got == exp, (n, log_gpus, a, inverse, fused)
