@@ -24,15 +24,16 @@ constexpr uint32_t kMaxDomainLog = 27;            // two tables of 2^27 - 1 twid
 //   LO0 = true : last pass (lo = 0): contiguous 2^TL-element tile = 2^(TL-S) blocks of 2^S, no adjacent-column bits;
 //   LO0 = false: upper pass: 2^S rows x 2^(TL-S) adjacent columns.
 // NT threads per CTA, MINB CTAs per SM (register cap via __launch_bounds__).
-template <int S, bool LO0, int NT, int MINB>
+template <int S, bool LO0, int NT, int MINB, int UNR = 1, bool PF = false>
 __global__ void __launch_bounds__(NT, MINB) k_ntt(const __grid_constant__ ntt_pass_params p, const fr_t* in, fr_t* out) {
   extern __shared__ uint4 smem[];
   const ntt_tile t{smem, smem + kTile};
   const uint64_t tile_id = p.tile_rot ? (blockIdx.x + p.tile_rot) % gridDim.x : blockIdx.x;
   const ntt_tile_ctx c = ntt_tile_begin(p, tile_id, (uint32_t)S, LO0 ? 0u : (uint32_t)(kNttTileLog - S),
                                         LO0 ? (uint32_t)(kNttTileLog - S) : 0u, LO0 ? 0u : p.lo);
-#pragma unroll 2
+#pragma unroll 4
   for (uint32_t pos = threadIdx.x; pos < kTile; pos += NT) ntt_tile_load(p, c, pos, in, t);
+  cp_async_wait_all();
   __syncthreads();
   constexpr uint32_t STEPS = (S + 1) / 2;
 #pragma unroll
@@ -43,11 +44,17 @@ __global__ void __launch_bounds__(NT, MINB) k_ntt(const __grid_constant__ ntt_pa
 #pragma unroll 1
       for (uint32_t q = threadIdx.x; q < kTile / 2; q += NT) ntt_step_r2(p, c, q, s, t);
     } else if (LO0 && s == 0) {
-#pragma unroll 1
+#pragma unroll UNR
       for (uint32_t q = threadIdx.x; q < kTile / 4; q += NT) ntt_step_r4<true>(p, c, q, s, t);
     } else {
-#pragma unroll 1
-      for (uint32_t q = threadIdx.x; q < kTile / 4; q += NT) ntt_step_r4<false>(p, c, q, s, t);
+#pragma unroll UNR
+      for (uint32_t q = threadIdx.x; q < kTile / 4; q += NT) {
+        if (PF) {            // twiddles of the thread's next group: same step, or the first group of the next step
+          if (q + NT < kTile / 4) ntt_prefetch_r4(p, c, q + NT, s);
+          else if (s >= 2 && !(LO0 && s == 2)) ntt_prefetch_r4(p, c, threadIdx.x, s - 2);
+        }
+        ntt_step_r4<false>(p, c, q, s, t);
+      }
     }
     __syncthreads();
   }
@@ -64,6 +71,7 @@ __global__ void __launch_bounds__(256, 2) k_ntt_generic(const __grid_constant__ 
   const uint64_t tile_id = p.tile_rot ? (blockIdx.x + p.tile_rot) % gridDim.x : blockIdx.x;
   const ntt_tile_ctx c = ntt_tile_begin(p, tile_id, p.S, p.g, p.x, p.lo);
   for (uint32_t pos = threadIdx.x; pos < tile; pos += blockDim.x) ntt_tile_load(p, c, pos, in, t);
+  cp_async_wait_all();
   __syncthreads();
   const uint32_t steps = ntt_pass_steps(p.S);
   const bool last_is_unit = p.lo == 0 && p.dist_shift == 0;
@@ -82,10 +90,13 @@ __global__ void __launch_bounds__(256, 2) k_ntt_generic(const __grid_constant__ 
   for (uint32_t pos = threadIdx.x; pos < tile; pos += blockDim.x) ntt_tile_store(p, c, pos, out, t);
 }
 
-// launch shape of the specialised kernels: threads per CTA / CTAs per SM (B381_NTT_SHAPE = 0..3 selects for A/B runs)
+// launch shape of the specialised kernels: 256 threads, 3 CTAs per SM (80 registers); B381_NTT_SHAPE=1 = 2 CTAs per SM
+// (up to 128 registers) for A/B runs.  Measured on B200 at 2^24 (profiles/r02_ntt_variants.txt): 3.60 ms vs 3.69 ms;
+// 128 or 512 threads, two groups per thread interleaved, and L1 prefetch of the next group's twiddles were all slower
+// or equal and are not built.
 struct ntt_shape { int nt, minb; };
 static int ntt_shape_id() {
-  static const int v = [] { const char* e = getenv("B381_NTT_SHAPE"); int x = e ? atoi(e) : 0; return x < 0 || x > 3 ? 0 : x; }();
+  static const int v = [] { const char* e = getenv("B381_NTT_SHAPE"); int x = e ? atoi(e) : 0; return x < 0 || x > 1 ? 0 : x; }();
   return v;
 }
 static bool ntt_force_generic() {
@@ -93,22 +104,20 @@ static bool ntt_force_generic() {
   return v;
 }
 
-template <int S, bool LO0, int NT, int MINB>
+template <int S, bool LO0, int NT, int MINB, int UNR = 1, bool PF = false>
 static void launch_k(const ntt_pass_params& p, const fr_t* in, fr_t* out, unsigned tiles, cudaStream_t st) {
   constexpr size_t smem = 2 * sizeof(uint4) * kTile;
   static bool attr_done = false;       // per instantiation
   if (!attr_done) {
-    cudaFuncSetAttribute(k_ntt<S, LO0, NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(k_ntt<S, LO0, NT, MINB, UNR, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     attr_done = true;
   }
-  k_ntt<S, LO0, NT, MINB><<<tiles, NT, smem, st>>>(p, in, out);
+  k_ntt<S, LO0, NT, MINB, UNR, PF><<<tiles, NT, smem, st>>>(p, in, out);
 }
 template <int S, bool LO0>
 static void launch_shape(const ntt_pass_params& p, const fr_t* in, fr_t* out, unsigned tiles, cudaStream_t st) {
   switch (ntt_shape_id()) {
     case 1: launch_k<S, LO0, 256, 2>(p, in, out, tiles, st); break;
-    case 2: launch_k<S, LO0, 512, 1>(p, in, out, tiles, st); break;
-    case 3: launch_k<S, LO0, 128, 3>(p, in, out, tiles, st); break;
     default: launch_k<S, LO0, 256, 3>(p, in, out, tiles, st); break;
   }
 }
@@ -127,8 +136,8 @@ static void launch_ntt_pass(const ntt_pass_params& p, const fr_t* in, fr_t* out,
   const bool full = tile_log == kNttTileLog && !ntt_force_generic();
   if (full && p.lo == 0 && p.dist_shift == 0 && p.g == 0 && p.S >= 1 && p.S <= kNttTileLog) {
     launch_s<true, (int)kNttTileLog>(p.S, p, in, out, tiles, st);
-  } else if (full && p.lo > 0 && p.x == 0 && p.S >= 1 && p.S <= kNttTileLog - 2) {
-    launch_s<false, (int)kNttTileLog - 2>(p.S, p, in, out, tiles, st);
+  } else if (full && p.lo > 0 && p.x == 0 && p.S >= 1 && p.S <= kNttTileLog - 1) {
+    launch_s<false, (int)kNttTileLog - 1>(p.S, p, in, out, tiles, st);
   } else {
     const size_t smem = (size_t)2 * sizeof(uint4) << tile_log;
     static bool attr_done = false;
@@ -347,7 +356,16 @@ static int ntt_run(const fr_t* input, int size, int dir, const b381_ntt_config* 
     if (!cfg->are_outputs_on_device && (e = sc.alloc(&d_out, total)) != cudaSuccess) return map_cuda_error(e);
 
     ntt_pass_plan plan[8];
-    const size_t P = (size_t)ntt_plan_passes(n, plan);
+    size_t P = 0;
+    if (const char* e = getenv("B381_NTT_PLAN")) {     // e.g. "10,10": stage counts, highest first (A/B runs only)
+      uint32_t S[8], cnt = 0;
+      for (const char* q = e; *q && cnt < 8;) {
+        S[cnt++] = (uint32_t)strtoul(q, const_cast<char**>(&q), 10);
+        if (*q == ',') q++;
+      }
+      P = (size_t)ntt_plan_from_list(n, S, cnt, plan);
+    }
+    if (P == 0) P = (size_t)ntt_plan_passes(n, plan);
     const bool inplace = (d_in == d_out);
     fr_t* work = d_out;
     if (P >= 2 && (perm_in || perm_out) && (inplace || perm_out)) {

@@ -191,10 +191,32 @@ B381_DI uint64_t ntt_addr(const ntt_pass_params& p, uint64_t I, bool permute) {
   return b * p.bstride + (uint64_t)i * p.estride;
 }
 
-// phase 1: slot `pos` <- global
+// 16-byte asynchronous copy global -> shared (LDGSTS): the tile load of a pass without a load-time scale keeps no
+// registers and no scoreboard slot per element, so every element of the thread is in flight at once
+B381_DI void cp_async16(void* smem_dst, const void* gsrc) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+#else
+  memcpy(smem_dst, gsrc, 16);
+#endif
+}
+B381_DI void cp_async_wait_all() {
+#if defined(__CUDA_ARCH__)
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+#endif
+}
+
+// phase 1: slot `pos` <- global  (followed by cp_async_wait_all() and the CTA barrier)
 B381_DI void ntt_tile_load(const ntt_pass_params& p, const ntt_tile_ctx& c, uint32_t pos, const fr_t* in, const ntt_tile& t) {
   uint64_t I = ntt_slot_index(c, pos);
   if (I >= p.total) return;
+  if (!p.pre_scale) {
+    const char* src = reinterpret_cast<const char*>(in + ntt_addr(p, I, p.perm_in != 0));
+    const uint32_t slot = ntt_tile_slot(pos);
+    cp_async16(t.lo + slot, src);
+    cp_async16(t.hi + slot, src + 16);
+    return;
+  }
   fr_t v = fr_gload(in + ntt_addr(p, I, p.perm_in != 0));
   if (p.pre_scale) v = mul(v, fr_gload_ro(p.pre_scale + (I & ((1ull << p.n) - 1))));
   tile_put(t, pos, v);
@@ -229,6 +251,25 @@ B381_DI void ntt_step_r2(const ntt_pass_params& p, const ntt_tile_ctx& c, uint32
   ntt_bfly(a, b, w);
   tile_put(t, pos0, a);
   tile_put(t, pos1, b);
+}
+
+B381_DI void prefetch_l1(const void* p) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+  (void)p;
+#endif
+}
+// pull the three twiddles of radix-4 group q (in-pass stages s+1, s) towards the SM ahead of their use
+B381_DI void ntt_prefetch_r4(const ntt_pass_params& p, const ntt_tile_ctx& c, uint32_t q, uint32_t s) {
+  const uint32_t bit0 = s + c.g;
+  const uint32_t base = ((q >> bit0) << (bit0 + 2)) | (q & ((1u << bit0) - 1));
+  const uint32_t k = c.jshift + s;
+  const uint32_t j0 = ntt_twiddle_j0(c, base, s);
+  const fr_t* Tk1 = p.twiddles + ((2ull << k) - 1) + j0;
+  prefetch_l1(p.twiddles + ((1ull << k) - 1) + j0);
+  prefetch_l1(Tk1);
+  prefetch_l1(Tk1 + (1ull << k));
 }
 
 // phase 2b: one radix-4 step = in-pass stages s+1 and s on group q of the tile's 2^(TL-2) quadruples: slots
@@ -332,6 +373,21 @@ struct ntt_pass_plan { uint32_t lo, S, g, x; };
 // contiguous) for coalescing.  Among the splits with the fewest passes, stage counts are balanced and EVEN where
 // possible (an odd count costs one extra radix-2 step = one more trip through shared memory): 24 -> 8 + 8 + 8,
 // 22 -> 6 + 8 + 8, 20 -> 9 + 11.  Fills `out` (capacity 8), highest stages first, and returns the number of passes.
+// explicit split (stage counts, highest stages first; sum must be n): experiments and tests
+inline int ntt_plan_from_list(uint32_t n, const uint32_t* S, uint32_t P, ntt_pass_plan* out, uint32_t tl = kNttTileLog) {
+  uint32_t hi = n, sum = 0;
+  for (uint32_t i = 0; i < P; i++) sum += S[i];
+  if (sum != n || P < 1 || P > 8) return 0;
+  for (uint32_t i = 0; i < P; i++) {
+    if (S[i] < 1 || S[i] > tl || (i + 1 < P && S[i] >= tl)) return 0;
+    if (i + 1 < P) out[i] = ntt_pass_plan{hi - S[i], S[i], tl - S[i], 0};
+    else out[i] = ntt_pass_plan{0, S[i], 0, tl - S[i]};
+    if (i + 1 < P && out[i].g > out[i].lo) return 0;
+    hi -= S[i];
+  }
+  return (int)P;
+}
+
 inline int ntt_plan_passes(uint32_t n, ntt_pass_plan* out, uint32_t tl = kNttTileLog) {
   int np = 0;
   if (n <= tl) {
@@ -342,13 +398,19 @@ inline int ntt_plan_passes(uint32_t n, ntt_pass_plan* out, uint32_t tl = kNttTil
   uint32_t P = 2;
   while ((P - 1) * up_max + tl < n) P++;
   uint32_t S[8];
-  // balanced start: every pass floor(n / P), remainder to the last passes; then make counts even by moving single
-  // stages between neighbours where the limits allow
-  for (uint32_t i = 0; i < P; i++) S[i] = n / P + ((i >= P - n % P) ? 1u : 0u);
-  auto ok = [&](uint32_t i, uint32_t v) { return v >= 1 && v <= (i + 1 == P ? tl : up_max); };
+  auto cap = [&](uint32_t i) { return i + 1 == P ? tl : up_max; };
+  // balanced start within the per-pass limits: every pass floor(n / P), remainder to the last passes, overflow of a
+  // capped pass handed on to the next one
+  uint32_t carry = 0;
+  for (uint32_t i = 0; i < P; i++) {
+    uint32_t want = n / P + ((i >= P - n % P) ? 1u : 0u) + carry;
+    S[i] = want > cap(i) ? cap(i) : want;
+    carry = want - S[i];
+  }
+  auto ok = [&](uint32_t i, uint32_t v) { return v >= 1 && v <= cap(i); };
+  // then make counts even by moving single stages between an odd pass and the next odd pass, where the limits allow
   for (uint32_t i = 0; i + 1 < P; i++) {
     if ((S[i] & 1) == 0) continue;
-    // find a later odd pass to pair with
     for (uint32_t j = i + 1; j < P; j++) {
       if (!(S[j] & 1)) continue;
       if (ok(i, S[i] - 1) && ok(j, S[j] + 1)) { S[i]--; S[j]++; }
