@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-I", CSRC, "-I", os.path.join(ROOT, "include"),
 ]
 
-CORE_SRCS = ["msm_g1.cu", "msm_g2.cu", "msm_pair.cu", "msm_tail.cu", "ntt.cu", "vecops.cu", "devapi.cu", "probes.cu", "pointgen.cu", "points.cu"]
+CORE_SRCS = ["msm_g1.cu", "msm_g2.cu", "msm_pair.cu", "msm_sort.cu", "msm_tail.cu", "ntt.cu", "vecops.cu", "devapi.cu", "probes.cu", "pointgen.cu", "points.cu"]
 ICICLE_FIELD_SRCS = ["icicle/field_api.cu"]
 ICICLE_CURVE_SRCS = ["icicle/curve_api.cu", "icicle/g2_registry.cu"]
 ICICLE_DEVICE_SRCS = ["icicle/device_api.cu"]
@@ -118,7 +118,7 @@ def build(verbose: bool = False, icicle: bool = True) -> dict[str, str]:
                                  pick(ICICLE_FIELD_SRCS) + [objs[s] for s in ("ntt.cu", "vecops.cu") if s in objs])
         if pick(ICICLE_CURVE_SRCS):
             out["curve"] = _link("libicicle_backend_cuda_curve_bls12_381.so",
-                                 pick(ICICLE_CURVE_SRCS) + [objs["points.cu"], objs["msm_g1.cu"], objs["msm_g2.cu"], objs["msm_pair.cu"], objs["msm_tail.cu"]])
+                                 pick(ICICLE_CURVE_SRCS) + [objs["points.cu"], objs["msm_g1.cu"], objs["msm_g2.cu"], objs["msm_pair.cu"], objs["msm_sort.cu"], objs["msm_tail.cu"]])
         if pick(ICICLE_DEVICE_SRCS):
             out["device"] = _link("libicicle_backend_cuda_device.so", pick(ICICLE_DEVICE_SRCS))
     return out

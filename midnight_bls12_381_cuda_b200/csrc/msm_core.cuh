@@ -4,14 +4,12 @@
 // checked without a GPU.
 //
 // Pipeline (ours; the reference's is bls12-381/src/curve/msm_kernels.cu:603-903):
-//   1 digits      scalar -> W signed c-bit digits -> (key = w*(B+1) + |d|-1, val = idx<<1 | sign);
-//                 zero digits go to the window's own trash bucket, key w*(B+1) + B
-//                                                           [ref: compute_bucket_indices_kernel :69-143]
-//   2 sort        keys are written window-major, so the data is already grouped by window: ONE radix sort
-//                 PER WINDOW over the c bits of the in-window key (2 onesweep passes at c = 16), or, for small
-//                 n / folded windows, one sort over ceil(log2(W*(B+1))) bits   [ref sorts all 32 bits, :768-778]
-//   3 offsets     bucket boundaries straight from the sorted keys (no histogram, no atomics)
-//                                                           [ref: histogram + scan, :224-256,:748-758]
+//   1 histogram   scalar -> W signed c-bit digits -> bucket slot key = w*(B+1) + |d|-1 (zero digits go to the
+//                 window's own trash slot w*(B+1) + B); hist[key]++   [ref: compute_bucket_indices_kernel :69-143]
+//   2 scan        bucket boundaries = exclusive scan of the histogram (own kernels, msm_sort.cu)
+//                                                           [ref: histogram of SORTED keys + scan, :224-256,:748-758]
+//   3 scatter     digits recomputed; vals[cursor[key]++] = idx<<1 | sign: a counting sort, no key array, no
+//                 library sort                              [ref: CUB radix sort of all 32 key bits, :768-778]
 //   3b pre-reduce affine pairwise levels with CTA-wide batched inversion (msm_batch.cuh): each level
 //                 halves every bucket at 6 Fq products per removed point      [no reference counterpart]
 //   4 tasks       every bucket is cut into ceil(size/K) equal tasks so one thread never owns more
@@ -77,66 +75,90 @@ B381_HD uint32_t msm_tasks_of(uint32_t size, uint32_t K) {
   return nt > kMaxTasksPerBucket ? kMaxTasksPerBucket : nt;
 }
 
-// ---------------------------------------------------------------- 1 digits
+// ---------------------------------------------------------------- 1 digits, 2 grouping by bucket
 // Signed-digit recoding with the same digit set as the reference
 // (msm_kernels.cu:96-130): d in [-(2^(c-1)-1), 2^(c-1)], d > 2^(c-1) => d -= 2^c, carry.
-// keys/vals are window-major ([w*n + i]) so stores coalesce.
-// local_keys: emit the in-window key only (0..B, B = trash) -- the per-window sort path (needs Wf == W).
-B381_DI void msm_digits_body(uint32_t i, const fr_t* scalars, bool scalars_mont, const msm_shape sh,
-                             uint32_t* keys, uint32_t* vals, bool local_keys = false) {
-  if (i >= sh.n) return;
-  fr_t s = scalars[i];
-  if (scalars_mont) s = from_mont(s);
-  const uint32_t mask = (1u << sh.c) - 1u;
-  uint32_t carry = 0;
-  for (uint32_t w = 0; w < sh.W; w++) {
-    uint32_t bit = w * sh.c;
-    uint32_t limb = bit >> 6, off = bit & 63;
-    uint32_t d = 0;
-    if (limb < 4) {
-      uint64_t lo = s.l[limb] >> off;
-      if (off + sh.c > 64 && limb + 1 < 4) lo |= s.l[limb + 1] << (64 - off);
-      d = (uint32_t)lo & mask;
-    }
-    d += carry;
-    carry = 0;
-    uint32_t sign = 0;
-    if (d > sh.B) {          // B = 2^(c-1)
-      d = (1u << sh.c) - d;
-      sign = 1;
-      carry = 1;
-    }
-    uint32_t blk = w / sh.Wf, wf = w - blk * sh.Wf;
-    uint32_t key = (local_keys ? 0u : wf * sh.Bs) + (d ? d - 1 : sh.B);
-    keys[(size_t)w * sh.n + i] = key;
-    vals[(size_t)w * sh.n + i] = ((i * sh.f + blk) << 1) | sign;
+// Digit w of canonical scalar s: bucket slot `key` = wf*Bs + |d|-1 (zero digits: the set's trash slot wf*Bs + B) and
+// entry `val` = (base index << 1) | sign.  `carry` runs from window 0 upwards.
+B381_DI void msm_digit_at(const fr_t& s, const msm_shape& sh, uint32_t i, uint32_t w, uint32_t& carry, uint32_t& key,
+                          uint32_t& val) {
+  const uint32_t bit = w * sh.c, limb = bit >> 6, off = bit & 63;
+  uint32_t d = 0;
+  if (limb < 4) {
+    uint64_t lo = s.l[limb] >> off;
+    if (off + sh.c > 64 && limb + 1 < 4) lo |= s.l[limb + 1] << (64 - off);
+    d = (uint32_t)lo & ((1u << sh.c) - 1u);
   }
+  d += carry;
+  carry = 0;
+  uint32_t sign = 0;
+  if (d > sh.B) {          // B = 2^(c-1)
+    d = (1u << sh.c) - d;
+    sign = 1;
+    carry = 1;
+  }
+  const uint32_t blk = w / sh.Wf, wf = w - blk * sh.Wf;
+  key = wf * sh.Bs + (d ? d - 1 : sh.B);
+  val = ((i * sh.f + blk) << 1) | sign;
   // W*c >= 256 > bit length of any canonical scalar, so the last carry is always 0.
 }
 
-// ---------------------------------------------------------------- 3 offsets
-// sorted keys -> offsets[0..nbuckets]; offsets[b] = first position with key >= b; offsets[nbuckets] = total.
-// n_local != 0: the keys are in-window keys, sorted per window slice of n_local entries; the bucket slot of
-// position j is (j / n_local) * Bs + key, which is monotone over the concatenated slices.
-// position j of the sorted keys, whose neighbours j-1 / j belong to windows w_prev / w_cur (per-window sort: keys
-// are in-window, the bucket-set base w * Bs is added here; 0 otherwise)
-B381_DI void msm_offsets_core(size_t j, uint32_t w_prev, uint32_t w_cur, const uint32_t* sorted_keys, size_t total,
-                              uint32_t nbuckets, uint32_t* offsets, uint32_t Bs) {
-  if (j > total) return;
-  uint32_t kp = 0, kc = 0;
-  if (j > 0) kp = sorted_keys[j - 1] + w_prev * Bs;
-  if (j < total) kc = sorted_keys[j] + w_cur * Bs;
-  uint32_t prev = (j == 0) ? 0u : kp + 1u;          // first key not yet started
-  uint32_t cur = (j == total) ? nbuckets + 1u : kc + 1u; // one past this key
-  // every bucket id in [prev, cur) starts at position j
-  for (uint32_t b = prev; b < cur && b <= nbuckets; b++) offsets[b] = (uint32_t)j;
+// counter += v, returning the old value: an L2 atomic on the device (RED when the result is unused), a plain
+// increment in the single-threaded host simulation
+B381_DI uint32_t msm_fetch_add(uint32_t* p, uint32_t v) {
+#ifdef B381_HOST_TEST
+  uint32_t o = *p;
+  *p = o + v;
+  return o;
+#else
+  return atomicAdd(p, v);
+#endif
 }
-B381_DI void msm_offsets_body(size_t j, const uint32_t* sorted_keys, size_t total, uint32_t nbuckets,
-                              uint32_t* offsets, uint32_t n_local = 0, uint32_t Bs = 0) {
-  if (j > total) return;
-  const uint32_t wp = (n_local && j > 0) ? (uint32_t)((j - 1) / n_local) : 0u;
-  const uint32_t wc = n_local ? (uint32_t)(j / n_local) : 0u;
-  msm_offsets_core(j, wp, wc, sorted_keys, total, nbuckets, offsets, n_local ? Bs : 0u);
+
+// The (bucket, point) pairs are grouped by a counting sort, hand-written because the keys are dense small integers
+// (nbuckets = Wf * (2^(c-1) + 1) slots) and only the GROUPING matters, not the order inside a bucket -- the bucket
+// sum is the same group element whatever the order, and the MSM result is its unique affine form:
+//   pass 1 (this body)   hist[key]++ for every (scalar, window)            -- 2^28 REDs at 2^24 points, 1.2 ms on B200
+//   scan                 offsets = exclusive scan of hist (msm_sort.cu)    -- these ARE the bucket boundaries
+//   pass 2 (next body)   vals[cursor[key]++] = val                         -- digits recomputed, no key array exists
+// The reference writes 2 x 32-bit keys/values per pair and radix-sorts all 32 key bits with CUB
+// (msm_kernels.cu:69-143, :768-778), then histograms the sorted keys with atomics (:224-256).
+B381_DI void msm_hist_body(uint32_t i, const fr_t* scalars, bool scalars_mont, const msm_shape sh, uint32_t* hist) {
+  if (i >= sh.n) return;
+  fr_t s = scalars[i];
+  if (scalars_mont) s = from_mont(s);
+  uint32_t carry = 0, key, val;
+  for (uint32_t w = 0; w < sh.W; w++) {
+    msm_digit_at(s, sh, i, w, carry, key, val);
+    msm_fetch_add(hist + key, 1u);
+  }
+}
+
+// pass 2: eight windows at a time so that eight returning atomics, then eight stores, are in flight per thread
+B381_DI void msm_scatter_body(uint32_t i, const fr_t* scalars, bool scalars_mont, const msm_shape sh, uint32_t* cursor,
+                              uint32_t* vals) {
+  if (i >= sh.n) return;
+  fr_t s = scalars[i];
+  if (scalars_mont) s = from_mont(s);
+  uint32_t carry = 0;
+  for (uint32_t w0 = 0; w0 < sh.W; w0 += 8) {
+    uint32_t key[8], val[8], pos[8];
+#ifndef B381_HOST_TEST
+#pragma unroll
+#endif
+    for (uint32_t j = 0; j < 8; j++)
+      if (w0 + j < sh.W) msm_digit_at(s, sh, i, w0 + j, carry, key[j], val[j]);
+#ifndef B381_HOST_TEST
+#pragma unroll
+#endif
+    for (uint32_t j = 0; j < 8; j++)
+      if (w0 + j < sh.W) pos[j] = msm_fetch_add(cursor + key[j], 1u);
+#ifndef B381_HOST_TEST
+#pragma unroll
+#endif
+    for (uint32_t j = 0; j < 8; j++)
+      if (w0 + j < sh.W) vals[pos[j]] = val[j];
+  }
 }
 
 // ---------------------------------------------------------------- 4 tasks
@@ -165,26 +187,21 @@ B381_DI void msm_build_tasks_body(uint32_t b, const uint32_t* offsets, const uin
   }
 }
 
-// sort key of task t for the longest-first visiting order: K - len (valid), K + 1 (unused slot)
-B381_DI void msm_task_key_body(uint32_t t, uint32_t max_tasks, uint32_t ntasks, const uint2* tasks, uint32_t K,
-                               uint32_t* keys, uint32_t* ids) {
-  if (t >= max_tasks) return;
-  uint32_t key = K + 1;
-  if (t < ntasks) {
-    uint2 tk = tasks[t];
-    uint32_t len = tk.y - tk.x;
-    key = len < K ? K - len : 0u;        // capped buckets have tasks longer than K: visit them first
-  }
-  keys[t] = key;
-  ids[t] = t;
+// Visiting order of the tasks: longest first, so the 32 tasks of a warp have near-equal lengths and the grid's tail
+// is made of the shortest ones.  Counting sort over the K + 1 keys K - len (msm_sort.cu); capped buckets have tasks
+// longer than K: key 0, visited first.
+B381_DI uint32_t msm_task_key(uint32_t t, const uint2* tasks, uint32_t K) {
+  const uint2 tk = tasks[t];
+  const uint32_t len = tk.y - tk.x;
+  return len < K ? K - len : 0u;
 }
 
 // ---------------------------------------------------------------- 5 accumulate (hot)
 template <class F>
 B381_DI void msm_accumulate_body(uint32_t t, uint32_t ntasks, const uint2* tasks, const uint32_t* sorted_vals,
                                  const affine_t<F>* bases, xyzz_t<F>* partial, const uint32_t* order = nullptr) {
-  if (order) t = order[t];              // tasks visited longest-first so a warp's 32 tasks have similar lengths
   if (t >= ntasks) return;
+  if (order) t = order[t];              // tasks visited longest-first so a warp's 32 tasks have similar lengths
   uint2 tk = tasks[t];
   xyzz_t<F> acc = xyzz_identity<F>();
   for (uint32_t j = tk.x; j < tk.y; j++) {

@@ -7,40 +7,16 @@
 // Replaces: msm::msm_cuda<S,A,P> (bls12-381/src/curve/msm_kernels.cu:603-903) and the ICICLE
 // wrappers msm_cuda_impl / msm_g2_cuda_impl / msm_precompute_bases_cuda_impl
 // (bls12-381/src/backend/icicle_curve_api.cu:243-407, :415-440, :454-650).
-#include <cub/device/device_radix_sort.cuh>
-#include <cub/device/device_scan.cuh>
-
 #include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 #include "msm_core.cuh"
+#include "msm_sort.cuh"
 
 namespace b381 {
 
 // ------------------------------------------------------------------ kernels
-static __global__ void k_msm_digits(const fr_t* scalars, bool mont, msm_shape sh, uint32_t* keys, uint32_t* vals,
-                                    bool local_keys) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_digits_body(i, scalars, mont, sh, keys, vals, local_keys);
-}
-
-static __global__ void k_msm_offsets(const uint32_t* sorted_keys, size_t total, uint32_t nbuckets, uint32_t* offsets,
-                                     uint32_t n_local, uint32_t Bs) {
-  size_t j = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  msm_offsets_body(j, sorted_keys, total, nbuckets, offsets, n_local, Bs);
-}
-
-// per-window sort: blockIdx.y is the window, so no thread divides a 64-bit position by n (that division made the
-// 1-D kernel run at 1.1 TB/s: 0.97 ms for the 2^28 keys of a 2^24-point MSM)
-static __global__ void k_msm_offsets_win(const uint32_t* sorted_keys, uint32_t n, uint32_t W, uint32_t nbuckets,
-                                         uint32_t* offsets, uint32_t Bs) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x, w = blockIdx.y;
-  if (i > n || (i == n && w + 1 != W)) return;       // position (w+1)*n belongs to thread (0, w+1)
-  const size_t j = (size_t)w * n + i;
-  msm_offsets_core(j, i > 0 ? w : w - 1, w, sorted_keys, (size_t)n * W, nbuckets, offsets, Bs);
-}
-
 static __global__ void k_msm_task_count(const uint32_t* offsets, uint32_t nbuckets, uint32_t Bs, uint32_t K,
                                         uint32_t* counts) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -52,12 +28,6 @@ static __global__ void k_msm_build_tasks(const uint32_t* offsets, const uint32_t
                                          uint32_t Bs, uint32_t K, uint2* tasks) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   msm_build_tasks_body(b, offsets, task_start, nbuckets, Bs, K, tasks);
-}
-
-static __global__ void k_msm_task_keys(uint32_t max_tasks, const uint32_t* ntasks_dev, const uint2* tasks, uint32_t K,
-                                uint32_t* keys, uint32_t* ids) {
-  uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_task_key_body(t, max_tasks, *ntasks_dev, tasks, K, keys, ids);
 }
 
 template <class F, int MINB = 1>
@@ -243,75 +213,22 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   size_t total = (size_t)n * sh.W;
   if (total >= (1ull << 31)) return cudaErrorInvalidValue;
 
-  // -- 1 digits
-  uint32_t *keys[2], *vals[2];
-  for (int i = 0; i < 2; i++) {
-    B381_CUDA_TRY(sc.alloc(&keys[i], total));
-    B381_CUDA_TRY(sc.alloc(&vals[i], total));
-  }
-  tm.mark();
-  // Keys are written window-major, so one sort PER WINDOW over the c bits of the in-window key does the job
-  // in ceil(c/8) onesweep passes (2 at c = 16) instead of ceil(log2(W*(B+1))/8) (3).  The W separate sorts cost
-  // ~0.8 ms of launches, so this pays from 2^23 points up (B200: 2^24 7.04 -> 5.65 ms, 2^22 1.81 -> 1.97 ms), and
-  // only when windows do not share bucket sets (no precomputed-bases folding).
-  bool per_window = sh.Wf == sh.W && n >= (1u << 23);
-  {
-    const char* e = getenv("B381_MSM_WINDOW_SORT");
-    if (e && e[0]) per_window = sh.Wf == sh.W && e[0] == '1';
-  }
-  k_msm_digits<<<grid_for(n, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, keys[0], vals[0], per_window);
-  tm.mark();
-
-  // -- 2 sort (only the significant key bits)
-  const uint32_t* skeys;
-  const uint32_t* svals;
-  if (per_window) {
-    const int key_bits = (int)sh.c;               // in-window keys 0 .. B = 2^(c-1)
-    size_t tmp_bytes = 0;
-    {
-      cub::DoubleBuffer<uint32_t> dk(keys[0], keys[1]), dv(vals[0], vals[1]);
-      B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)n, 0, key_bits, st));
-    }
-    uint8_t* tmp = nullptr;
-    B381_CUDA_TRY(sc.alloc(&tmp, tmp_bytes));
-    int sel = -1;
-    for (uint32_t w = 0; w < sh.W; w++) {
-      const size_t o = (size_t)w * n;
-      cub::DoubleBuffer<uint32_t> dk(keys[0] + o, keys[1] + o), dv(vals[0] + o, vals[1] + o);
-      B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)n, 0, key_bits, st));
-      const int s_w = dk.Current() == keys[1] + o ? 1 : 0;
-      if (sel < 0) sel = s_w;
-      if (s_w != sel) {        // same size and bit count for every window: the selector cannot differ; be safe anyway
-        B381_CUDA_TRY(cudaMemcpyAsync(keys[sel] + o, keys[s_w] + o, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
-        B381_CUDA_TRY(cudaMemcpyAsync(vals[sel] + o, vals[s_w] + o, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, st));
-      }
-    }
-    skeys = keys[sel];
-    svals = vals[sel];
-  } else {
-    cub::DoubleBuffer<uint32_t> dk(keys[0], keys[1]), dv(vals[0], vals[1]);
-    int key_bits = (int)ceil_log2_u64((uint64_t)sh.nbuckets);
-    if (key_bits < 1) key_bits = 1;
-    size_t tmp_bytes = 0;
-    B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, (int)total, 0, key_bits, st));
-    uint8_t* tmp = nullptr;
-    B381_CUDA_TRY(sc.alloc(&tmp, tmp_bytes));
-    B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, (int)total, 0, key_bits, st));
-    skeys = dk.Current();
-    svals = dv.Current();
-  }
-  tm.mark();
-
-  // -- 3 offsets
-  uint32_t *offsets, *counts, *task_start;
+  // -- 1 histogram of the bucket slots, 2 scan = bucket boundaries, 3 scatter (msm_sort.cu; no library sort)
+  int launches = 0;
+  uint32_t *vals, *hist, *offsets, *counts, *task_start;
+  B381_CUDA_TRY(sc.alloc(&vals, total));
+  B381_CUDA_TRY(sc.alloc(&hist, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(sc.alloc(&offsets, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(sc.alloc(&counts, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(sc.alloc(&task_start, (size_t)sh.nbuckets + 1));
-  if (per_window)
-    k_msm_offsets_win<<<dim3(grid_for((size_t)n + 1, 256), sh.W), 256, 0, st>>>(skeys, n, sh.W, sh.nbuckets, offsets, sh.Bs);
-  else
-    k_msm_offsets<<<grid_for(total + 1, 256), 256, 0, st>>>(skeys, total, sh.nbuckets, offsets, 0u, sh.Bs);
   tm.mark();
+  B381_CUDA_TRY(msm_histogram(sc, d_scalars, scalars_mont, sh, hist));
+  launches++;
+  tm.mark();
+  B381_CUDA_TRY(msm_group_pairs(sc, d_scalars, scalars_mont, sh, hist, offsets, vals, &launches));
+  const uint32_t* svals = vals;
+  tm.mark();
+  tm.mark();     // (phase slot kept: "offsets" was a separate pass over the sorted keys in round 1)
 
   // -- 3b affine pre-reduction levels (msm_batch.cuh): each halves every bucket
   const affine_t<F>* acc_pts = d_bases;
@@ -353,11 +270,8 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
       B381_CUDA_TRY(sc.alloc(&half, (size_t)sh.nbuckets + 1));
       B381_CUDA_TRY(sc.alloc(&out_off, (size_t)sh.nbuckets + 1));
       k_msm_half_counts<<<grid_for((size_t)sh.nbuckets + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, sh.Bs, half);
-      size_t sb = 0;
-      B381_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, sb, half, out_off, (int)sh.nbuckets + 1, st));
-      uint8_t* stmp = nullptr;
-      B381_CUDA_TRY(sc.alloc(&stmp, sb));
-      B381_CUDA_TRY(cub::DeviceScan::ExclusiveSum(stmp, sb, half, out_off, (int)sh.nbuckets + 1, st));
+      B381_CUDA_TRY(exclusive_scan_u32(sc, half, out_off, (size_t)sh.nbuckets + 1, nullptr, &launches));
+      launches += 4;      // half counts + forward, invert, backward
       const unsigned g = grid_for(max_out, (size_t)PR_TPB * PB);
       if (!buf[l & 1]) B381_CUDA_TRY(sc.alloc(&buf[l & 1], nt_buf[l & 1] * PB));   // ping-pong
       if (!srcg) {
@@ -391,35 +305,19 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
     if (e && atoi(e) > 0) K = (uint32_t)atoi(e);
   }
   k_msm_task_count<<<grid_for((size_t)sh.nbuckets + 1, 256), 256, 0, st>>>(offsets, sh.nbuckets, sh.Bs, K, counts);
-  size_t scan_bytes = 0;
-  B381_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, counts, task_start, (int)sh.nbuckets + 1, st));
-  uint8_t* scan_tmp = nullptr;
-  B381_CUDA_TRY(sc.alloc(&scan_tmp, scan_bytes));
-  B381_CUDA_TRY(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, counts, task_start, (int)sh.nbuckets + 1, st));
+  B381_CUDA_TRY(exclusive_scan_u32(sc, counts, task_start, (size_t)sh.nbuckets + 1, nullptr, &launches));
   const size_t max_tasks = (size_t)sh.nbuckets + total / K + 1;
   uint2* tasks;
   B381_CUDA_TRY(sc.alloc(&tasks, max_tasks));
   k_msm_build_tasks<<<grid_for(sh.nbuckets, 256), 256, 0, st>>>(offsets, task_start, sh.nbuckets, sh.Bs, K, tasks);
-  // visiting order: longest task first (radix sort of K - len over just enough bits), so the 32 tasks of a
-  // warp have near-equal lengths and the grid's tail is made of the shortest ones
-  const uint32_t* order = nullptr;
+  // visiting order: longest task first (counting sort by task length, msm_sort.cu), so the 32 tasks of a warp have
+  // near-equal lengths and the grid's tail is made of the shortest ones
+  uint32_t* order = nullptr;
   {
     const char* e = getenv("B381_MSM_NO_TASK_SORT");
     if (!(e && e[0] == '1')) {
-      uint32_t *tk[2], *ti[2];
-      for (int i = 0; i < 2; i++) {
-        B381_CUDA_TRY(sc.alloc(&tk[i], max_tasks));
-        B381_CUDA_TRY(sc.alloc(&ti[i], max_tasks));
-      }
-      k_msm_task_keys<<<grid_for(max_tasks, 256), 256, 0, st>>>((uint32_t)max_tasks, task_start + sh.nbuckets, tasks, K, tk[0], ti[0]);
-      cub::DoubleBuffer<uint32_t> bk(tk[0], tk[1]), bi(ti[0], ti[1]);
-      int bits = (int)ceil_log2_u64((uint64_t)K + 2);
-      size_t tb = 0;
-      B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tb, bk, bi, (int)max_tasks, 0, bits, st));
-      uint8_t* ttmp = nullptr;
-      B381_CUDA_TRY(sc.alloc(&ttmp, tb));
-      B381_CUDA_TRY(cub::DeviceRadixSort::SortPairs(ttmp, tb, bk, bi, (int)max_tasks, 0, bits, st));
-      order = bi.Current();
+      B381_CUDA_TRY(sc.alloc(&order, max_tasks));
+      B381_CUDA_TRY(msm_task_order(sc, max_tasks, task_start + sh.nbuckets, tasks, K, order, &launches));
     }
   }
 
@@ -462,10 +360,10 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   {
     int tree = 0;
     for (uint32_t half = segs / 2; half >= 1; half >>= 1) tree++;
-    // digits, offsets (CUB sorts not counted) | 4 per level (+ the offsets copy is a memcpy) | task_count, build_tasks, task_keys,
-    // accumulate, finalize | segment, tree levels, combine
+    // counted above: histogram, scans, scatter, 4 per level + its scan, task order; here: task_count, build_tasks,
+    // accumulate, finalize (2) | segment, tree levels, combine
     g_last_info[0] = (int)sh.c; g_last_info[1] = (int)sh.W; g_last_info[2] = n_levels;
-    g_last_info[3] = 2 + 4 * n_levels + 6 + 1 + tree + 1;
+    g_last_info[3] = launches + 5 + 1 + tree + 1;
   }
   B381_CUDA_TRY(cudaGetLastError());
   tm.finish();

@@ -1,6 +1,6 @@
 // CPU-only driver for the per-thread MSM bodies in csrc/msm_core.cuh (TEST INFRASTRUCTURE).
 // Runs exactly the kernel pipeline of csrc/msm_impl.cuh with a serial loop per "kernel" and
-// std::stable_sort in place of the device radix sort.  Usage:
+// a serial exclusive scan in place of the device scan.  Usage:
 //   msm_host_sim <g1|g2> <n> <c> <K> <L> <scalars_mont 0|1> <infile> [factor] [levels]; prints result hex (std form)
 // levels > 0 runs that many affine pre-reduction levels (csrc/msm_batch.cuh) before the tasks, 3 output
 // slots per simulated thread; forward, batched inversion of the thread totals and backward run as the three
@@ -36,23 +36,17 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint
     pts.swap(ex);
   }
   size_t total = (size_t)n * sh.W;
-  std::vector<uint32_t> keys(total), vals(total);
-  // n odd + unfolded windows: exercise the per-window sort path (in-window keys, one sort per window slice)
-  const bool per_window = sh.Wf == sh.W && (n & 1);
-  for (uint32_t i = 0; i < n; i++) msm_digits_body(i, sc.data(), mont, sh, keys.data(), vals.data(), per_window);
-  std::vector<size_t> perm(total);
-  std::iota(perm.begin(), perm.end(), 0);
-  if (per_window) {
-    for (uint32_t w = 0; w < sh.W; w++)
-      std::stable_sort(perm.begin() + (size_t)w * n, perm.begin() + (size_t)(w + 1) * n,
-                       [&](size_t a, size_t b) { return keys[a] < keys[b]; });
-  } else {
-    std::stable_sort(perm.begin(), perm.end(), [&](size_t a, size_t b) { return keys[a] < keys[b]; });
-  }
-  std::vector<uint32_t> sk(total), sv(total);
-  for (size_t j = 0; j < total; j++) { sk[j] = keys[perm[j]]; sv[j] = vals[perm[j]]; }
-  std::vector<uint32_t> offsets(sh.nbuckets + 1, 0xdeadbeef);
-  for (size_t j = 0; j <= total; j++) msm_offsets_body(j, sk.data(), total, sh.nbuckets, offsets.data(), per_window ? n : 0u, sh.Bs);
+  // counting sort exactly as msm_sort.cu runs it: histogram, exclusive scan, scatter through per-slot cursors.  The
+  // "threads" of the scatter pass run in a scrambled order (odd n: descending) because the device gives no ordering
+  // guarantee inside a bucket and nothing downstream may depend on one.
+  std::vector<uint32_t> hist(sh.nbuckets + 1, 0), offsets(sh.nbuckets + 1, 0xdeadbeef), sv(total, 0xdeadbeef);
+  for (uint32_t i = 0; i < n; i++) msm_hist_body(i, sc.data(), mont, sh, hist.data());
+  uint32_t run = 0;
+  for (uint32_t b = 0; b <= sh.nbuckets; b++) { offsets[b] = run; run += hist[b]; }
+  if (offsets[sh.nbuckets] != total) return 4;
+  std::vector<uint32_t> cursor(offsets);
+  for (uint32_t i = 0; i < n; i++) msm_scatter_body((n & 1) ? n - 1 - i : i, sc.data(), mont, sh, cursor.data(), sv.data());
+  for (uint32_t b = 0; b < sh.nbuckets; b++) if (cursor[b] != offsets[b + 1]) return 5;
   // affine pre-reduction levels
   const uint32_t* cur_vals = sv.data();
   std::vector<affine_t<F>> lvl_pts;
