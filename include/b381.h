@@ -206,6 +206,17 @@ int bls12_381_g2_projective_to_affine(const b381_g2_projective* in, int size, co
 /* flags[i] = 1 if point i is infinity or satisfies y^2 = x^3 + 4 (G1) / y^2 = x^3 + 4(1+u) (G2), else 0 */
 int b381_g1_is_on_curve(const b381_g1_affine* in, int size, const b381_vecops_config* config, uint8_t* flags);
 int b381_g2_is_on_curve(const b381_g2_affine* in, int size, const b381_vecops_config* config, uint8_t* flags);
+/* flags[i] = 1 if point i (assumed on the curve) lies in the order-r subgroup: phi(P) = [z^2 - 1] P on G1,
+ * psi(P) = [z] P on G2 (csrc/glv.cuh); infinity counts as a member.  The reference leaves both checks as TODO
+ * (include/point.cuh:419-448). */
+int b381_g1_is_in_subgroup(const b381_g1_affine* in, int size, const b381_vecops_config* config, uint8_t* flags);
+int b381_g2_is_in_subgroup(const b381_g2_affine* in, int size, const b381_vecops_config* config, uint8_t* flags);
+/* out[i] = scalars[i] * bases[i]  (bls12-381/src/curve/point_ops.cu:1019-1268; same names, argument order and codes):
+ * bases Montgomery affine (is_a_on_device), scalars CANONICAL integers (is_b_on_device), out Jacobian Montgomery,
+ * always the normalised representative (x, y, 1) / (0, R, 0).  _glv splits k = k1 + k2 * lambda with the G1
+ * endomorphism (128 doublings instead of 252); the plain variant is its comparator. */
+int bls12_381_g1_scalar_mul_glv(const b381_g1_affine* bases, const b381_fr* scalars, int size, const b381_vecops_config* config, b381_g1_projective* out);
+int bls12_381_g1_scalar_mul(const b381_g1_affine* bases, const b381_fr* scalars, int size, const b381_vecops_config* config, b381_g1_projective* out);
 
 /* ======================= device plumbing (CudaDeviceAPI, src/device/cuda_device_api.cu:38-149) ==== */
 int b381_device_count(int* count);

@@ -77,6 +77,7 @@ EXPORTS = [
     "bls12_381_vector_add", "bls12_381_vector_sub", "bls12_381_vector_mul",
     "bls12_381_g1_affine_to_projective", "bls12_381_g1_projective_to_affine", "bls12_381_g2_affine_to_projective",
     "bls12_381_g2_projective_to_affine", "b381_g1_is_on_curve", "b381_g2_is_on_curve",
+    "b381_g1_is_in_subgroup", "b381_g2_is_in_subgroup", "bls12_381_g1_scalar_mul_glv", "bls12_381_g1_scalar_mul",
     "b381_vector_sum", "b381_vector_inv", "b381_bit_reverse", "b381_montgomery_convert",
     "vec_add_cuda", "vec_sub_cuda", "vec_mul_cuda", "scalar_mul_vec_cuda", "scalar_add_vec_cuda", "vec_sum_cuda",
     "b381_device_count", "b381_set_device", "b381_malloc", "b381_malloc_async", "b381_free", "b381_free_async",

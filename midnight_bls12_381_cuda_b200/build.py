@@ -29,7 +29,7 @@ NVCC_FLAGS = [
     "-I", CSRC, "-I", os.path.join(ROOT, "include"),
 ]
 
-CORE_SRCS = ["msm_g1.cu", "msm_g2.cu", "msm_pair.cu", "msm_sort.cu", "msm_tail.cu", "ntt.cu", "vecops.cu", "devapi.cu", "probes.cu", "pointgen.cu", "points.cu"]
+CORE_SRCS = ["msm_g1.cu", "msm_g2.cu", "msm_pair.cu", "msm_sort.cu", "msm_tail.cu", "ntt.cu", "vecops.cu", "devapi.cu", "probes.cu", "pointgen.cu", "points.cu", "point_mul.cu"]
 ICICLE_FIELD_SRCS = ["icicle/field_api.cu"]
 ICICLE_CURVE_SRCS = ["icicle/curve_api.cu", "icicle/g2_registry.cu"]
 ICICLE_DEVICE_SRCS = ["icicle/device_api.cu"]

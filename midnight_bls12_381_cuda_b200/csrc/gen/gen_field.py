@@ -364,6 +364,59 @@ def constants() -> str:
     # Fr: 2^32-th root of unity 7^((r-1)/2^32), Montgomery form
     w = pow(7, (FR.m - 1) >> 32, FR.m)
     out.append(f"#define FR_ROOT_OF_UNITY_MONT_INIT {_c64(w * FR.R % FR.m, 4)}")
+    # --- endomorphisms (point_mul.cu).  All derived here from the BLS parameter z; oracle/pyref.py derives them again
+    # on its own and tests/test_oracle.py compares the two.
+    z = -0xD201000000010000
+    assert FR.m == z**4 - z**2 + 1
+    out.append(f"#define BLS_Z_ABS 0x{-z:016x}ull          /* |z|; z is negative */")
+    # G1: phi(x, y) = (beta x, y) acts on the order-r subgroup as multiplication by lambda = z^2 - 1, and
+    # r = lambda^2 + lambda + 1 exactly, so  k = k1 + k2 lambda  with  k2 = floor(k / lambda), k1 = k mod lambda  < 2^128.
+    lam = z * z - 1
+    assert lam * lam + lam + 1 == FR.m and lam.bit_length() == 128
+    gx = 2
+    while pow(gx, (FQ.m - 1) // 3, FQ.m) == 1:
+        gx += 1
+    beta = pow(gx, (FQ.m - 1) // 3, FQ.m)
+    # of the two primitive cube roots pick the one with phi(G) = [lambda] G
+    def _aff_add(P, Q):
+        if P is None: return Q
+        if Q is None: return P
+        (x1, y1), (x2, y2) = P, Q
+        if x1 == x2:
+            if (y1 + y2) % FQ.m == 0: return None
+            l = 3 * x1 * x1 * pow(2 * y1, -1, FQ.m) % FQ.m
+        else:
+            l = (y2 - y1) * pow(x2 - x1, -1, FQ.m) % FQ.m
+        x3 = (l * l - x1 - x2) % FQ.m
+        return (x3, (l * (x1 - x3) - y1) % FQ.m)
+    def _mul(k, P):
+        R = None
+        while k:
+            if k & 1: R = _aff_add(R, P)
+            P = _aff_add(P, P); k >>= 1
+        return R
+    lg = _mul(lam, (g1x, g1y))
+    if (beta * g1x % FQ.m, g1y) != lg:
+        beta = beta * beta % FQ.m
+    assert (beta * g1x % FQ.m, g1y) == lg
+    out.append(f"#define GLV_BETA_MONT_INIT {_c64(beta * FQ.R % FQ.m, 6)}")
+    out.append(f"#define GLV_LAMBDA_INIT {_c64(lam, 2)}")
+    out.append(f"#define GLV_RECIP_INIT {_c64((1 << 256) // lam, 3)}          /* floor(2^256 / lambda), 129 bits */")
+    # G2: psi(x, y) = (conj(x) / xi^((p-1)/3), conj(y) / xi^((p-1)/2)), xi = 1 + u (untwist-Frobenius-twist); acts on the
+    # order-r subgroup as multiplication by z  (checked against [z] G2 in tests/test_oracle.py)
+    def f2mul(a, b): return ((a[0] * b[0] - a[1] * b[1]) % FQ.m, (a[0] * b[1] + a[1] * b[0]) % FQ.m)
+    def f2pow(a, e):
+        r = (1, 0)
+        while e:
+            if e & 1: r = f2mul(r, a)
+            a = f2mul(a, a); e >>= 1
+        return r
+    def f2inv(a):
+        n = pow(a[0] * a[0] + a[1] * a[1], -1, FQ.m)
+        return (a[0] * n % FQ.m, -a[1] * n % FQ.m)
+    for name, e in (("PSI_CX", (FQ.m - 1) // 3), ("PSI_CY", (FQ.m - 1) // 2)):
+        c = f2inv(f2pow((1, 1), e))
+        out.append(f"#define {name}_MONT_INIT {{{_c64(c[0] * FQ.R % FQ.m, 6)}, {_c64(c[1] * FQ.R % FQ.m, 6)}}}")
     out.append("")
     return "\n".join(out) + "\n"
 

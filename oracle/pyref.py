@@ -291,6 +291,122 @@ def g2_msm(scalars, points):
 
 
 # --------------------------------------------------------------------------
+# endomorphisms and subgroup membership (ground truth for csrc/glv.cuh).  The reference has only the constants
+# (bls12-381/src/curve/point_ops.cu:103-142) and TODOs for the checks (include/point.cuh:419-448).
+# --------------------------------------------------------------------------
+def curve_mul_unreduced(k: int, P):
+    """[k] P for ANY point of the curve (k is NOT reduced mod r: the point need not have order r).  P is a pair of
+    _Fq or Fq2 coordinates or None."""
+    R = None
+    Q = P
+    while k:
+        if k & 1:
+            R = _aff_add(R, Q)
+        Q = _aff_add(Q, Q)
+        k >>= 1
+    return R
+
+
+GLV_LAMBDA = BLS_X * BLS_X - 1                          # eigenvalue of phi on G1; r = lambda^2 + lambda + 1
+assert GLV_LAMBDA * GLV_LAMBDA + GLV_LAMBDA + 1 == R_MOD
+
+
+def _glv_beta() -> int:
+    g = 2
+    while pow(g, (P_MOD - 1) // 3, P_MOD) == 1:
+        g += 1
+    b = pow(g, (P_MOD - 1) // 3, P_MOD)
+    lg = _u1(curve_mul_unreduced(GLV_LAMBDA, _w1(G1_GEN)))
+    for cand in (b, b * b % P_MOD):
+        if (cand * G1_X % P_MOD, G1_Y) == lg:
+            return cand
+    raise AssertionError("no cube root of unity matches lambda")
+
+
+GLV_BETA = _glv_beta()                                  # phi(x, y) = (beta x, y) = [lambda](x, y) on G1
+
+
+def glv_decompose(k: int):
+    """k = k1 + k2 * lambda with 0 <= k1 < lambda, 0 <= k2 <= lambda + 1."""
+    k2, k1 = divmod(k % R_MOD, GLV_LAMBDA)
+    return k1, k2
+
+
+def g1_in_subgroup(P) -> bool:
+    """ground truth: [r] P = O"""
+    return P is None or curve_mul_unreduced(R_MOD, _w1(P)) is None
+
+
+def g2_in_subgroup(P) -> bool:
+    return P is None or curve_mul_unreduced(R_MOD, P) is None
+
+
+def fq2_pow(a: "Fq2", e: int) -> "Fq2":
+    r = Fq2(1, 0)
+    while e:
+        if e & 1:
+            r = r * a
+        a = a * a
+        e >>= 1
+    return r
+
+
+PSI_CX = fq2_pow(Fq2(1, 1), (P_MOD - 1) // 3).inv()       # psi(x, y) = (conj(x) PSI_CX, conj(y) PSI_CY)
+PSI_CY = fq2_pow(Fq2(1, 1), (P_MOD - 1) // 2).inv()
+
+
+def g2_psi(P):
+    if P is None:
+        return None
+    x, y = P
+    return (Fq2(x.c0, -x.c1) * PSI_CX, Fq2(y.c0, -y.c1) * PSI_CY)
+
+
+def fq_sqrt(a: int):
+    """square root in Fq (p = 3 mod 4) or None"""
+    a %= P_MOD
+    y = pow(a, (P_MOD + 1) // 4, P_MOD)
+    return y if y * y % P_MOD == a else None
+
+
+def fq2_sqrt(a: "Fq2"):
+    """square root in Fq2 = Fq[u]/(u^2+1), p = 3 mod 4 (complex method), or None"""
+    if a.is_zero():
+        return a
+    n = fq_sqrt(a.c0 * a.c0 + a.c1 * a.c1)              # norm must be a square in Fq
+    if n is None:
+        return None
+    inv2 = pow(2, -1, P_MOD)
+    for nn in (n, -n):
+        d = fq_sqrt((a.c0 + nn) * inv2)
+        if d is None or d == 0:
+            continue
+        c = Fq2(d, a.c1 * pow(2 * d, -1, P_MOD))
+        if c * c == a:
+            return c
+    return None
+
+
+def g1_curve_point(seed: int):
+    """a point of E(Fq): y^2 = x^3 + 4 that is (with overwhelming probability) NOT in the order-r subgroup"""
+    x = seed
+    while True:
+        y = fq_sqrt(x * x * x + 4)
+        if y is not None:
+            return (x % P_MOD, y)
+        x += 1
+
+
+def g2_curve_point(seed: int):
+    x = Fq2(seed, 1)
+    while True:
+        y = fq2_sqrt(x * x * x + G2_B)
+        if y is not None:
+            return (x, y)
+        x = x + Fq2(1, 0)
+
+
+# --------------------------------------------------------------------------
 # wire encodings of points
 # --------------------------------------------------------------------------
 def g1_affine_mont_bytes(P) -> bytes:

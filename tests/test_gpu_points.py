@@ -108,3 +108,86 @@ def test_on_curve_and_argument_errors(cuda, b381):
     cfg = lib.b381_default_vecops_config()
     assert lib.bls12_381_g1_projective_to_affine(None, 4, C.byref(cfg), b381.ptr(flags)) == 11
     assert lib.bls12_381_g1_projective_to_affine(b381.ptr(flags), 0, C.byref(cfg), b381.ptr(flags)) == 11
+
+
+# ---------------------------------------------------------------- endomorphisms: GLV scalar multiplication, subgroup checks
+def test_g1_scalar_mul_glv_and_plain(cuda, b381):
+    """bls12_381_g1_scalar_mul_glv / bls12_381_g1_scalar_mul (point_ops.cu:1019-1268): out[i] = k_i * P_i, canonical
+    scalars, Montgomery affine bases; both paths against big-integer k * P, byte for byte in the normalised Jacobian
+    form, host and device residency, including the scalars at the edges of the k = k1 + k2 * lambda split."""
+    import vectors_points as V
+    rng = P.SplitMix64(4242)
+    ks = V.glv_scalars() + [rng.fr() for _ in range(34)]
+    n = len(ks)
+    base_pts = [P.g1_mul(rng.fr(), P.G1_GEN) for _ in range(16)]
+    pts = [base_pts[i % 16] for i in range(n)]
+    pts[5] = None
+    bases = np.frombuffer(b"".join(P.g1_affine_mont_bytes(p) for p in pts), dtype=np.uint64).copy()
+    sc = np.frombuffer(b"".join(P.fr_bytes(k % P.R_MOD) for k in ks), dtype=np.uint64).copy()
+    exp = b"".join(g1_jac_bytes(P.g1_mul(k, p), 1) for k, p in zip(ks, pts))
+    lib = b381.lib()
+    for name in ("bls12_381_g1_scalar_mul_glv", "bls12_381_g1_scalar_mul"):
+        cfg = lib.b381_default_vecops_config()
+        out = np.zeros(18 * n, dtype=np.uint64)
+        assert getattr(lib, name)(b381.ptr(bases), b381.ptr(sc), n, C.byref(cfg), b381.ptr(out)) == 0
+        assert out.tobytes() == exp, name
+        cfg.is_a_on_device = cfg.is_b_on_device = cfg.is_result_on_device = True
+        d_b, d_s = cuda.from_numpy(bases.view(np.int64)).cuda(), cuda.from_numpy(sc.view(np.int64)).cuda()
+        d_o = cuda.zeros(18 * n, dtype=cuda.int64, device="cuda")
+        assert getattr(lib, name)(b381.ptr(d_b), b381.ptr(d_s), n, C.byref(cfg), b381.ptr(d_o)) == 0
+        assert d_o.cpu().numpy().tobytes() == exp, name
+        assert getattr(lib, name)(None, b381.ptr(sc), n, C.byref(cfg), b381.ptr(out)) == 11
+        assert getattr(lib, name)(b381.ptr(bases), b381.ptr(sc), 0, C.byref(cfg), b381.ptr(out)) == 11
+
+
+def test_g1_scalar_mul_glv_matches_msm(cuda, b381):
+    """sum of the GLV products == the MSM over the same inputs (two independent code paths), 2^12 points"""
+    n = 1 << 12
+    lib = b381.lib()
+    g = np.frombuffer(P.g1_affine_mont_bytes(P.G1_GEN), dtype=np.uint64).copy()
+    bases = cuda.empty((n, 12), dtype=cuda.int64, device="cuda")
+    assert lib.b381_g1_point_series(b381.ptr(g), b381.ptr(g), C.c_uint64(n), b381.ptr(bases), None) == 0
+    sc_int = fr_ints_local(n, 99)
+    sc = cuda.from_numpy(np.frombuffer(b"".join(P.fr_bytes(k) for k in sc_int), dtype=np.uint64).copy().view(np.int64)).cuda()
+    cfg = lib.b381_default_vecops_config()
+    cfg.is_a_on_device = cfg.is_b_on_device = cfg.is_result_on_device = True
+    prods = cuda.zeros((n, 18), dtype=cuda.int64, device="cuda")
+    assert lib.bls12_381_g1_scalar_mul_glv(b381.ptr(bases), b381.ptr(sc), n, C.byref(cfg), b381.ptr(prods)) == 0
+    # spot check 8 products against big integers, and the sum against the discrete log
+    host = prods.cpu().numpy().view(np.uint64)
+    for i in (0, 1, 77, 500, 1023, 2048, 4000, n - 1):
+        assert host[i].tobytes() == g1_jac_bytes(P.g1_mul(sc_int[i] * (i + 1), P.G1_GEN), 1)
+    mcfg = lib.b381_default_msm_config()
+    mcfg.are_scalars_on_device = mcfg.are_points_on_device = True
+    mcfg.are_points_montgomery_form = True
+    res = np.zeros(18, dtype=np.uint64)
+    assert lib.b381_g1_msm(b381.ptr(sc), b381.ptr(bases), n, C.byref(mcfg), b381.ptr(res)) == 0
+    dl = sum(k * (i + 1) for i, k in enumerate(sc_int)) % P.R_MOD
+    assert res.tobytes() == P.g1_result_std_bytes(P.g1_mul(dl, P.G1_GEN))
+
+
+def fr_ints_local(n, seed):
+    rng = P.SplitMix64(seed)
+    return [rng.fr() for _ in range(n)]
+
+
+def test_subgroup_checks(cuda, b381):
+    """b381_g1_is_in_subgroup / b381_g2_is_in_subgroup against [r]P == O computed with big integers: members,
+    infinity, random curve points, pure cofactor-subgroup points (one of order 3), member + non-member sums."""
+    import vectors_points as V
+    lib = b381.lib()
+    for name, cases, enc, words in (("b381_g1_is_in_subgroup", V.g1_membership_cases(), P.g1_affine_mont_bytes, 12),
+                                    ("b381_g2_is_in_subgroup", V.g2_membership_cases(), P.g2_affine_mont_bytes, 24)):
+        cases = cases * 3                         # more than one warp's worth of mixed outcomes
+        n = len(cases)
+        raw = np.frombuffer(b"".join(enc(p) for p, _ in cases), dtype=np.uint64).copy()
+        flags = np.full(n, 7, dtype=np.uint8)
+        assert call(b381, name, raw, n, flags) == 0
+        assert list(flags) == [int(m) for _, m in cases], name
+        d_in = cuda.from_numpy(raw.view(np.int64)).cuda()
+        d_f = cuda.zeros(n, dtype=cuda.uint8, device="cuda")
+        assert call(b381, name, d_in, n, d_f, on_device=True) == 0
+        assert list(d_f.cpu().numpy()) == [int(m) for _, m in cases], name
+        cfg = lib.b381_default_vecops_config()
+        assert getattr(lib, name)(None, n, C.byref(cfg), b381.ptr(flags)) == 11
+        assert getattr(lib, name)(b381.ptr(raw), -1, C.byref(cfg), b381.ptr(flags)) == 11

@@ -209,3 +209,59 @@ def test_ntt_distributed_columns(sims, n, log_gpus, a, tile_log):
             raw = bytes.fromhex(r.stdout.strip())
             got = [P.fr_from_mont(int.from_bytes(raw[32 * i:32 * i + 32], "little")) for i in range(1 << n)]
             assert got == exp, (n, log_gpus, a, inverse, fused)
+
+
+# ---------------------------------------------------------------- csrc/glv.cuh: GLV split, scalar multiplication, subgroup checks
+@pytest.fixture(scope="module")
+def glv_sim(tmp_path_factory):
+    out = tmp_path_factory.mktemp("glvsim")
+    exe = str(out / "glv_host_sim")
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-I{HOST}", f"-I{CSRC}", "-o", exe, os.path.join(HOST, "glv_host_sim.cpp")],
+                   check=True)
+    return exe, str(out)
+
+
+def test_glv_decomposition(glv_sim):
+    import vectors_points as V
+    exe, d = glv_sim
+    ks = V.glv_scalars()
+    path = os.path.join(d, "k.bin")
+    with open(path, "wb") as f:
+        for k in ks:
+            f.write(P.fr_bytes(k % P.R_MOD))
+    lines = subprocess.run([exe, "decompose", path], capture_output=True, text=True, check=True).stdout.split("\n")
+    for k, ln in zip(ks, lines):
+        k1, k2 = (int(x, 16) for x in ln.split())
+        assert (k1, k2) == P.glv_decompose(k), hex(k)
+        assert k1 + k2 * P.GLV_LAMBDA == k % P.R_MOD and k1 < P.GLV_LAMBDA
+
+
+def test_glv_scalar_mul_bodies(glv_sim):
+    import vectors_points as V
+    exe, d = glv_sim
+    rng = P.SplitMix64(384)
+    ks = V.glv_scalars()[:20]
+    pts = [P.g1_mul(rng.fr(), P.G1_GEN) for _ in ks]
+    pts[3] = None
+    path = os.path.join(d, "m.bin")
+    with open(path, "wb") as f:
+        for k, pt in zip(ks, pts):
+            f.write(P.g1_affine_mont_bytes(pt) + P.fr_bytes(k % P.R_MOD))
+    exp = [P.g1_affine_mont_bytes(P.g1_mul(k, pt)).hex() for k, pt in zip(ks, pts)]
+    for glv in ("1", "0"):
+        got = subprocess.run([exe, "mul", glv, path], capture_output=True, text=True, check=True).stdout.split()
+        assert got == exp, glv
+
+
+def test_subgroup_check_bodies(glv_sim):
+    import vectors_points as V
+    exe, d = glv_sim
+    for group, cases, enc in (("g1", V.g1_membership_cases(), P.g1_affine_mont_bytes),
+                              ("g2", V.g2_membership_cases(), P.g2_affine_mont_bytes)):
+        assert any(m for _, m in cases) and any(not m for _, m in cases)
+        path = os.path.join(d, group + ".bin")
+        with open(path, "wb") as f:
+            for pt, _ in cases:
+                f.write(enc(pt))
+        got = subprocess.run([exe, "sub", group, path], capture_output=True, text=True, check=True).stdout.split()
+        assert [int(x) for x in got] == [int(m) for _, m in cases], group

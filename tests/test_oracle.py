@@ -173,3 +173,38 @@ def test_poly_eval_pins_ntt_outputs(oracle):
     w = P.fr_omega(18)
     for i in (3, n // 2 + 1, n - 1):
         assert (oracle.poly_eval(a, mont([pow(w, i, P.R_MOD)])[0]) == y[i]).all()
+
+
+def test_endomorphism_constants():
+    """The constants csrc/gen/gen_field.py writes for csrc/glv.cuh equal the ones oracle/pyref.py derives on its own;
+    beta and lambda also equal the literals the reference carries (bls12-381/src/curve/point_ops.cu:120-133:
+    GLV_BETA Montgomery, GLV_LAMBDA), and phi / psi act as [lambda] / [z] on the generators."""
+    import os
+    import re
+    hdr = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "midnight_bls12_381_cuda_b200",
+                            "csrc", "field_consts.h")).read()
+
+    def limbs(name):
+        body = re.search(r"#define " + name + r" (.*)", hdr).group(1).split("/*")[0]
+        return [int(x, 16) for x in re.findall(r"0x([0-9a-f]+)ull", body)]
+
+    assert P.from_limbs(limbs("GLV_BETA_MONT_INIT")) == P.fq_to_mont(P.GLV_BETA)
+    assert limbs("GLV_BETA_MONT_INIT") == [0xcd03c9e48671f071, 0x5dab22461fcda5d2, 0x587042afd3851b95, 0x8eb60ebe01bacb9e,
+                                           0x03f97d6e83d050d2, 0x18f0206554638741]
+    assert P.from_limbs(limbs("GLV_LAMBDA_INIT")) == P.GLV_LAMBDA == 0xac45a4010001a40200000000ffffffff
+    assert P.from_limbs(limbs("GLV_RECIP_INIT")) == (1 << 256) // P.GLV_LAMBDA
+    assert limbs("BLS_Z_ABS")[0] == -P.BLS_X
+    cx, cy = limbs("PSI_CX_MONT_INIT"), limbs("PSI_CY_MONT_INIT")
+    assert (P.from_limbs(cx[:6]), P.from_limbs(cx[6:])) == (P.fq_to_mont(P.PSI_CX.c0), P.fq_to_mont(P.PSI_CX.c1))
+    assert (P.from_limbs(cy[:6]), P.from_limbs(cy[6:])) == (P.fq_to_mont(P.PSI_CY.c0), P.fq_to_mont(P.PSI_CY.c1))
+    assert pow(P.GLV_BETA, 3, P.P_MOD) == 1 and P.GLV_BETA != 1
+    k = 0x1234567
+    pt = P.g1_mul(k, P.G1_GEN)
+    assert (pt[0] * P.GLV_BETA % P.P_MOD, pt[1]) == P.g1_mul(P.GLV_LAMBDA, pt)
+    q = P.g2_mul(k, P.G2_GEN)
+    zq = P.g2_mul(P.BLS_X % P.R_MOD, q)
+    psi = P.g2_psi(q)
+    assert psi[0] == zq[0] and psi[1] == zq[1] and P.g2_on_curve(psi)
+    # ground truth of the membership tests: random curve points are not members, generator multiples are
+    assert P.g1_on_curve(P.g1_curve_point(3)) and not P.g1_in_subgroup(P.g1_curve_point(3)) and P.g1_in_subgroup(pt)
+    assert P.g2_on_curve(P.g2_curve_point(5)) and not P.g2_in_subgroup(P.g2_curve_point(5)) and P.g2_in_subgroup(q)
