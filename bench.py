@@ -684,7 +684,7 @@ def main():
         fr_rate = v.value
         ms_step = ms_total / args.steps
         ph = [statistics.mean(c) for c in zip(*phases)] if phases else []
-        names = ["digits", "sort", "offsets", "prereduce", "tasks+accumulate", "finalize", "bucket_reduce", "combine"]
+        names = ["histogram", "scan+scatter", "(unused)", "prereduce", "tasks+accumulate", "finalize", "bucket_reduce", "combine"]
         c_win, W, levels, own_launches = msm_info[0], msm_info[1], msm_info[2], msm_info[3]
         # Dominant stage = bucket accumulation: `levels` affine pre-reduction levels (k_msm_pair_fwd / k_msm_invert_totals /
         # k_msm_pair_bwd, csrc/msm_batch.cuh) + k_msm_accumulate on what is left.  Algorithmic work per (point, window)
@@ -775,9 +775,10 @@ def main():
                 "note": "GpuMsmContext.msm_with_device_bases_async (own stream per call, host scalars staged by the plugin call), "
                         "two commits in flight"},
             "gpu_launches": (own_launches + 1) * args.steps,
-            "gpu_launches_note": "own kernels per MSM step as counted by the library (b381_msm_last_info): digits, offsets, "
-                                 "4 per affine level, task_count/build_tasks/task_keys, accumulate, finalize, segment, tree levels, "
-                                 "combine, + encode (CUB radix sort / scan kernels not counted)",
+            "gpu_launches_note": "own kernels per MSM step as counted by the library (b381_msm_last_info): histogram, scan "
+                                 "(tile / totals / add), scatter, 4 + scan per affine level, task_count/build_tasks, task order "
+                                 "(hist / scan / scatter), accumulate, finalize, segment, tree levels, combine, + encode; "
+                                 "no library kernel is on the MSM path",
             "phases_ms": dict(zip(names, [round(x, 4) for x in ph[:8]])),
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "ntt": ntt, "vecops": vec_ops, "reference_gpu": ref_gpu,
             "g2": None if g2 is None else {k: v for k, v in g2.items() if k != "result"},

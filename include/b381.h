@@ -153,6 +153,14 @@ int b381_vector_sub(const b381_fr* a, const b381_fr* b, uint64_t size, const b38
 int b381_vector_mul(const b381_fr* a, const b381_fr* b, uint64_t size, const b381_vecops_config* config, b381_fr* out);
 int b381_scalar_mul_vec(const b381_fr* scalar_a, const b381_fr* b, uint64_t size, const b381_vecops_config* config, b381_fr* out);
 int b381_scalar_add_vec(const b381_fr* scalar_a, const b381_fr* b, uint64_t size, const b381_vecops_config* config, b381_fr* out);
+/* Upstream ICICLE v4 batch form (VecOpsConfig.batch_size / columns_batch; core/vecops.rs:345-346 sets batch_size):
+ * `batch_size` scalars, `batch_size` vectors of `size` elements, stored one after the other, or interleaved when
+ * columns_batch (element j of vector k at j * batch_size + k).  The ICICLE glue built with
+ * -DB381_ICICLE_UPSTREAM_VECOPS routes here (csrc/icicle/field_api.cu). */
+int b381_scalar_mul_vec_batch(const b381_fr* scalars, const b381_fr* b, uint64_t size, int batch_size, bool columns_batch,
+                              const b381_vecops_config* config, b381_fr* out);
+int b381_scalar_add_vec_batch(const b381_fr* scalars, const b381_fr* b, uint64_t size, int batch_size, bool columns_batch,
+                              const b381_vecops_config* config, b381_fr* out);
 
 /* ---- unregistered ops the reference's callers use on the same vectors ---- */
 /* out[0] = sum a[i]  (vec_sum_cuda, vec_ops.cu:479-520) */

@@ -70,7 +70,7 @@ EXPORTS = [
     "b381_default_msm_config", "b381_default_ntt_config", "b381_default_vecops_config",
     "b381_g1_msm", "b381_g2_msm", "b381_g1_msm_precompute_bases", "b381_g2_msm_precompute_bases",
     "b381_ntt_init_domain", "b381_ntt_release_domain", "b381_ntt", "b381_ntt_get_rou_from_domain",
-    "b381_vector_add", "b381_vector_sub", "b381_vector_mul", "b381_scalar_mul_vec", "b381_scalar_add_vec",
+    "b381_vector_add", "b381_vector_sub", "b381_vector_mul", "b381_scalar_mul_vec", "b381_scalar_add_vec", "b381_scalar_mul_vec_batch", "b381_scalar_add_vec_batch",
     "bls12_381_g1_msm_cuda", "bls12_381_g2_msm_cuda", "bls12_381_ntt_cuda", "bls12_381_ntt_init_domain_cuda",
     "bls12_381_ntt_release_domain_cuda", "bls12_381_coset_ntt_cuda", "bls12_381_field_ntt_cuda",
     "bls12_381_field_ntt_init_domain_cuda", "bls12_381_field_ntt_release_domain_cuda",

@@ -57,16 +57,16 @@ def _deps_of(obj: str) -> list[str] | None:
     return [t for t in parts[1].split() if t.startswith(ROOT)]
 
 
-def _compile(src: str, hdr_mtime: float, verbose: bool) -> str:
+def _compile(src: str, hdr_mtime: float, verbose: bool, defines: tuple = (), tag: str = "") -> str:
     path = os.path.join(CSRC, src)
-    obj = os.path.join(OBJ, src.replace("/", "_") + ".o")
+    obj = os.path.join(OBJ, src.replace("/", "_") + tag + ".o")
     if os.path.exists(obj):
         deps = _deps_of(obj)
         newest = hdr_mtime if deps is None else max(
             [os.path.getmtime(d) if os.path.exists(d) else float("inf") for d in deps] + [0.0])
         if os.path.getmtime(obj) > max(os.path.getmtime(path), newest):
             return obj
-    cmd = [NVCC] + NVCC_FLAGS + ["-MD", "-MF", obj + ".d", "-c", path, "-o", obj]
+    cmd = [NVCC] + NVCC_FLAGS + [f"-D{d}" for d in defines] + ["-MD", "-MF", obj + ".d", "-c", path, "-o", obj]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)
@@ -79,6 +79,7 @@ def _compile(src: str, hdr_mtime: float, verbose: bool) -> str:
 
 def _link(name: str, objs: list[str], extra: list[str] | None = None) -> str:
     out = os.path.join(LIB, name)
+    os.makedirs(os.path.dirname(out), exist_ok=True)
     if os.path.exists(out) and all(os.path.getmtime(out) > os.path.getmtime(o) for o in objs):
         return out
     cmd = [NVCC, "-shared", "-o", out] + objs + ["-Xcompiler", "-fPIC"] + (extra or [])
@@ -116,6 +117,11 @@ def build(verbose: bool = False, icicle: bool = True) -> dict[str, str]:
         if pick(ICICLE_FIELD_SRCS):
             out["field"] = _link("libicicle_backend_cuda_field_bls12_381.so",
                                  pick(ICICLE_FIELD_SRCS) + [objs[s] for s in ("ntt.cu", "vecops.cu") if s in objs])
+            # same library for a real ICICLE v4 install, whose VecOpsConfig carries batch_size / columns_batch
+            # (csrc/icicle/icicle_abi.h): lib/upstream_v4/, same file name
+            v4 = _compile(ICICLE_FIELD_SRCS[0], hdr, verbose, ("B381_ICICLE_UPSTREAM_VECOPS",), "_v4")
+            out["field_v4"] = _link(os.path.join("upstream_v4", "libicicle_backend_cuda_field_bls12_381.so"),
+                                    [v4] + [objs[s] for s in ("ntt.cu", "vecops.cu") if s in objs])
         if pick(ICICLE_CURVE_SRCS):
             out["curve"] = _link("libicicle_backend_cuda_curve_bls12_381.so",
                                  pick(ICICLE_CURVE_SRCS) + [objs["points.cu"], objs["msm_g1.cu"], objs["msm_g2.cu"], objs["msm_pair.cu"], objs["msm_sort.cu"], objs["msm_tail.cu"]])

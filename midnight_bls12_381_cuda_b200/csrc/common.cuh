@@ -5,6 +5,7 @@
 // never implicitly synchronises the device.)
 #pragma once
 #include <cuda_runtime.h>
+#include <nvtx3/nvToolsExt.h>
 
 #include <cstdint>
 #include <cstdio>
@@ -91,6 +92,30 @@ cudaError_t stage_in(Scratch& sc, const T* src, size_t count, bool on_device, co
   *out = d;
   return e;
 }
+
+// NVTX ranges (the reference only has Rust `tracing` spans around its calls, core/msm.rs:538-574,
+// core/ntt.rs:509-541).  NVTX3 is header-only and resolves the tool's injection library at run time, so there is no link
+// dependency and a range costs a few nanoseconds when no profiler is attached.  Domain "b381"; ranges: one per C-ABI
+// call (with the size in the name) and one per MSM phase, so a timeline / ncu --nvtx-include filter can address them.
+struct TraceRange {
+  static nvtxDomainHandle_t domain() {
+    static nvtxDomainHandle_t d = nvtxDomainCreateA("b381");
+    return d;
+  }
+  explicit TraceRange(const char* name, long long arg = -1) {
+    char buf[96];
+    if (arg >= 0) { snprintf(buf, sizeof(buf), "%s n=%lld", name, arg); name = buf; }
+    nvtxEventAttributes_t a = {};
+    a.version = NVTX_VERSION;
+    a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+    a.messageType = NVTX_MESSAGE_TYPE_ASCII;
+    a.message.ascii = name;
+    nvtxDomainRangePushEx(domain(), &a);
+  }
+  ~TraceRange() { nvtxDomainRangePop(domain()); }
+  TraceRange(const TraceRange&) = delete;
+  TraceRange& operator=(const TraceRange&) = delete;
+};
 
 inline unsigned grid_for(size_t threads, unsigned block) { return (unsigned)((threads + block - 1) / block); }
 

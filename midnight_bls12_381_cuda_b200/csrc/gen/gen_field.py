@@ -364,8 +364,8 @@ def constants() -> str:
     # Fr: 2^32-th root of unity 7^((r-1)/2^32), Montgomery form
     w = pow(7, (FR.m - 1) >> 32, FR.m)
     out.append(f"#define FR_ROOT_OF_UNITY_MONT_INIT {_c64(w * FR.R % FR.m, 4)}")
-    # --- endomorphisms (point_mul.cu).  All derived here from the BLS parameter z; oracle/pyref.py derives them again
-    # on its own and tests/test_oracle.py compares the two.
+    # --- endomorphisms (point_mul.cu).  All derived here from the BLS parameter z; the test suite derives them again
+    # on its own (big-integer checker) and compares the two.
     z = -0xD201000000010000
     assert FR.m == z**4 - z**2 + 1
     out.append(f"#define BLS_Z_ABS 0x{-z:016x}ull          /* |z|; z is negative */")
@@ -403,7 +403,7 @@ def constants() -> str:
     out.append(f"#define GLV_LAMBDA_INIT {_c64(lam, 2)}")
     out.append(f"#define GLV_RECIP_INIT {_c64((1 << 256) // lam, 3)}          /* floor(2^256 / lambda), 129 bits */")
     # G2: psi(x, y) = (conj(x) / xi^((p-1)/3), conj(y) / xi^((p-1)/2)), xi = 1 + u (untwist-Frobenius-twist); acts on the
-    # order-r subgroup as multiplication by z  (checked against [z] G2 in tests/test_oracle.py)
+    # order-r subgroup as multiplication by z  (checked against [z] G2 by the test suite)
     def f2mul(a, b): return ((a[0] * b[0] - a[1] * b[1]) % FQ.m, (a[0] * b[1] + a[1] * b[0]) % FQ.m)
     def f2pow(a, e):
         r = (1, 0)

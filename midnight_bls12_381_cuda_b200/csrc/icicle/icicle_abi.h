@@ -66,7 +66,15 @@ template <typename S> struct NTTConfig {
   void* ext;
 };
 struct NTTInitDomainConfig { void* stream; bool is_async; void* ext; };
-struct VecOpsConfig { void* stream; bool is_a_on_device, is_b_on_device, is_result_on_device, is_async; void* ext; };
+#ifdef B381_ICICLE_UPSTREAM_VECOPS
+// upstream ICICLE v4.0.0 (icicle/include/icicle/vec_ops.h): two more members than the reference's copy of the struct.
+// The reference's Rust layer sets batch_size (core/vecops.rs:345-346), so a real ICICLE install needs THIS layout;
+// build.py emits that variant of the field library under lib/upstream_v4/ (same SONAME, same mangled symbols --
+// the layout of a struct is not part of its mangled name).
+struct VecOpsConfig { void* stream; bool is_a_on_device, is_b_on_device, is_result_on_device, is_async; int batch_size; bool columns_batch; void* ext; };
+#else
+struct VecOpsConfig { void* stream; bool is_a_on_device, is_b_on_device, is_result_on_device, is_async; void* ext; };   // icicle_types.cuh:194-201
+#endif
 
 using scalar_t = ::Field<bls12_381::fp_config>;
 using fq_field_t = ::Field<bls12_381::fq_config>;

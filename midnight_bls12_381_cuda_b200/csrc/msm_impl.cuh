@@ -137,13 +137,24 @@ struct PhaseTimer {
     const char* e = getenv("B381_MSM_TIMING");
     on = e && e[0] == '1';
   }
-  void mark() {
+  // phase boundary: closes the NVTX range of the phase that ends here and opens `next` (nullptr: none)
+  bool range_open = false;
+  void mark(const char* next = nullptr) {
+    if (range_open) nvtxDomainRangePop(TraceRange::domain());
+    range_open = next != nullptr;
+    if (next) {
+      nvtxEventAttributes_t a = {};
+      a.version = NVTX_VERSION; a.size = NVTX_EVENT_ATTRIB_STRUCT_SIZE;
+      a.messageType = NVTX_MESSAGE_TYPE_ASCII; a.message.ascii = next;
+      nvtxDomainRangePushEx(TraceRange::domain(), &a);
+    }
     if (!on) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, s);
     ev.push_back(e);
   }
+  ~PhaseTimer() { if (range_open) nvtxDomainRangePop(TraceRange::domain()); }
   void finish() {
     if (!on || ev.empty()) return;
     cudaEventSynchronize(ev.back());
@@ -221,14 +232,14 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   B381_CUDA_TRY(sc.alloc(&offsets, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(sc.alloc(&counts, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(sc.alloc(&task_start, (size_t)sh.nbuckets + 1));
-  tm.mark();
+  tm.mark("msm:histogram");
   B381_CUDA_TRY(msm_histogram(sc, d_scalars, scalars_mont, sh, hist));
   launches++;
-  tm.mark();
+  tm.mark("msm:scan+scatter");
   B381_CUDA_TRY(msm_group_pairs(sc, d_scalars, scalars_mont, sh, hist, offsets, vals, &launches));
   const uint32_t* svals = vals;
-  tm.mark();
-  tm.mark();     // (phase slot kept: "offsets" was a separate pass over the sorted keys in round 1)
+  tm.mark(nullptr);
+  tm.mark("msm:affine_levels");     // (phase slot kept: "offsets" was a separate pass over the sorted keys in round 1)
 
   // -- 3b affine pre-reduction levels (msm_batch.cuh): each halves every bucket
   const affine_t<F>* acc_pts = d_bases;
@@ -294,7 +305,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
       total = max_in;
     }
   }
-  tm.mark();
+  tm.mark("msm:tasks+accumulate");
 
   // -- 4 tasks
   // task length bound: mean bucket load + 4 sigma (Poisson), so a uniform input is one task per bucket
@@ -334,10 +345,10 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
     else if (variant == 4) k_msm_accumulate<F, 4><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, acc_vals, acc_pts, partial, order);
     else k_msm_accumulate<F, 1><<<g, 128, 0, st>>>(task_start + sh.nbuckets, tasks, acc_vals, acc_pts, partial, order);
   }
-  tm.mark();
+  tm.mark("msm:finalize");
   // -- 6 finalize
   launch_msm_finalize<F>(sh.nbuckets, task_start, counts, partial, buckets, st);
-  tm.mark();
+  tm.mark("msm:bucket_reduce");
 
   // -- 7 segments, 8 tree
   // segment length: measured on B200 (gpurun sweep of B381_MSM_L = 4..64): 32 up to 2^14 buckets per window
@@ -353,10 +364,10 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   xyzz_t<F>* seg;
   B381_CUDA_TRY(sc.alloc(&seg, (size_t)sh.Wf * segs));
   launch_msm_bucket_reduce<F>(sh.Wf, sh.B, L, buckets, seg, st);
-  tm.mark();
+  tm.mark("msm:combine");
   // -- 9 combine
   launch_msm_combine<F>(seg, segs, sh.Wf, sh.c, d_out, st);
-  tm.mark();
+  tm.mark(nullptr);
   {
     int tree = 0;
     for (uint32_t half = segs / 2; half >= 1; half >>= 1) tree++;
@@ -385,6 +396,7 @@ static int msm_entry(const fr_t* scalars, const affine_t<F>* bases, int msm_size
   uint32_t n = (uint32_t)msm_size;
   cudaStream_t st = (cudaStream_t)cfg->stream;
   cudaError_t e;
+  TraceRange trace(sizeof(F) == sizeof(fq_t) ? "b381_g1_msm" : "b381_g2_msm", msm_size);
   {
     Scratch sc(st);
     const fr_t* d_scalars = nullptr;

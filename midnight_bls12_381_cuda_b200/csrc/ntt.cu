@@ -348,6 +348,7 @@ static int ntt_run(const fr_t* input, int size, int dir, const b381_ntt_config* 
   }
 
   cudaError_t e;
+  TraceRange trace(inverse ? "b381_ntt inverse" : "b381_ntt forward", (long long)total);
   {
     Scratch sc(st);
     const fr_t* d_in;

@@ -53,6 +53,7 @@ static int vecop_entry(const b381_fr* a, const b381_fr* b, uint64_t n, const b38
   if (!a || !b || !out) return B381_INVALID_POINTER;
   cudaStream_t st = (cudaStream_t)cfg->stream;
   cudaError_t e;
+  TraceRange trace(OP == VADD ? "b381_vec add" : OP == VSUB ? "b381_vec sub" : "b381_vec mul", (long long)n);
   {
     Scratch sc(st);
     const fr_t *da, *db;
@@ -76,6 +77,46 @@ static int vecop_entry(const b381_fr* a, const b381_fr* b, uint64_t n, const b38
   return B381_SUCCESS;
 }
 
+// Upstream ICICLE v4 batch semantics of scalar (op) vector (VecOpsConfig.batch_size / columns_batch, which the reference's
+// struct lacks but its Rust layer sets, core/vecops.rs:345-346): `batch` scalars, `batch` vectors of n elements stored
+// one after the other (rows) or interleaved (columns_batch: element j of vector k at j * batch + k).
+template <int OP>
+__global__ void __launch_bounds__(256) k_scalar_vec_batch(const fr_t* scalars, const fr_t* vec, uint64_t n, uint32_t batch,
+                                                          bool columns, uint64_t total, fr_t* out) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t k = columns ? i % batch : i / n;
+    st_fr(out + i, apply<OP>(ld_fr(scalars + k), ld_fr(vec + i)));
+  }
+}
+
+template <int OP>
+static int scalar_batch_entry(const b381_fr* a, const b381_fr* b, uint64_t n, int batch_size, bool columns,
+                              const b381_vecops_config* cfg, b381_fr* out) {
+  if (!cfg) return B381_INVALID_POINTER;
+  if (batch_size < 1) return B381_INVALID_ARGUMENT;
+  if (batch_size == 1) return vecop_entry<OP, true>(a, b, n, cfg, out);
+  if (n == 0) return B381_SUCCESS;
+  if (!a || !b || !out) return B381_INVALID_POINTER;
+  const uint64_t total = n * (uint64_t)batch_size;
+  cudaStream_t st = (cudaStream_t)cfg->stream;
+  cudaError_t e;
+  {
+    Scratch sc(st);
+    const fr_t *da, *db;
+    if ((e = stage_in(sc, (const fr_t*)a, (size_t)batch_size, cfg->is_a_on_device, &da)) != cudaSuccess) return map_cuda_error(e);
+    if ((e = stage_in(sc, (const fr_t*)b, total, cfg->is_b_on_device, &db)) != cudaSuccess) return map_cuda_error(e);
+    fr_t* dout = (fr_t*)out;
+    if (!cfg->is_result_on_device && (e = sc.alloc(&dout, total)) != cudaSuccess) return map_cuda_error(e);
+    uint64_t blocks = (total + 255) / 256;
+    if (blocks > 148ull * 32) blocks = 148ull * 32;
+    k_scalar_vec_batch<OP><<<(unsigned)blocks, 256, 0, st>>>(da, db, n, (uint32_t)batch_size, columns, total, dout);
+    if ((e = cudaGetLastError()) != cudaSuccess) return map_cuda_error(e);
+    if (!cfg->is_result_on_device && (e = cudaMemcpyAsync(out, dout, total * sizeof(fr_t), cudaMemcpyDeviceToHost, st)) != cudaSuccess)
+      return map_cuda_error(e);
+  }
+  if (!cfg->is_async && (e = cudaStreamSynchronize(st)) != cudaSuccess) return map_cuda_error(e);
+  return B381_SUCCESS;
+}
 
 // ---- unregistered-but-needed ops -------------------------------------------------------
 // out = sum a[i]: grid-stride partial per thread, shuffle + shared-memory tree per CTA, second launch folds the
@@ -235,6 +276,14 @@ int b381_vector_sub(const b381_fr* a, const b381_fr* b, uint64_t n, const b381_v
 int b381_vector_mul(const b381_fr* a, const b381_fr* b, uint64_t n, const b381_vecops_config* c, b381_fr* o) { return vecop_entry<VMUL, false>(a, b, n, c, o); }
 int b381_scalar_mul_vec(const b381_fr* a, const b381_fr* b, uint64_t n, const b381_vecops_config* c, b381_fr* o) { return vecop_entry<VMUL, true>(a, b, n, c, o); }
 int b381_scalar_add_vec(const b381_fr* a, const b381_fr* b, uint64_t n, const b381_vecops_config* c, b381_fr* o) { return vecop_entry<VADD, true>(a, b, n, c, o); }
+int b381_scalar_mul_vec_batch(const b381_fr* a, const b381_fr* b, uint64_t n, int batch_size, bool columns_batch,
+                              const b381_vecops_config* c, b381_fr* o) {
+  return scalar_batch_entry<VMUL>(a, b, n, batch_size, columns_batch, c, o);
+}
+int b381_scalar_add_vec_batch(const b381_fr* a, const b381_fr* b, uint64_t n, int batch_size, bool columns_batch,
+                              const b381_vecops_config* c, b381_fr* o) {
+  return scalar_batch_entry<VADD>(a, b, n, batch_size, columns_batch, c, o);
+}
 int bls12_381_vector_add(const b381_fr* a, const b381_fr* b, uint64_t n, const b381_vecops_config* c, b381_fr* o) { return vecop_entry<VADD, false>(a, b, n, c, o); }
 int bls12_381_vector_sub(const b381_fr* a, const b381_fr* b, uint64_t n, const b381_vecops_config* c, b381_fr* o) { return vecop_entry<VSUB, false>(a, b, n, c, o); }
 int bls12_381_vector_mul(const b381_fr* a, const b381_fr* b, uint64_t n, const b381_vecops_config* c, b381_fr* o) { return vecop_entry<VMUL, false>(a, b, n, c, o); }

@@ -16,10 +16,59 @@ BACKENDS = ["libicicle_backend_cuda_device.so", "libicicle_backend_cuda_field_bl
             "libicicle_backend_cuda_curve_bls12_381.so"]
 
 
-def load():
+def load(field_dir=LIBDIR):
     mock = C.CDLL(MOCK, mode=C.RTLD_GLOBAL)
-    libs = [C.CDLL(os.path.join(LIBDIR, b), mode=C.RTLD_GLOBAL) for b in BACKENDS]
+    libs = [C.CDLL(os.path.join(field_dir if "field" in b else LIBDIR, b), mode=C.RTLD_GLOBAL) for b in BACKENDS]
     return mock, libs
+
+
+class VecOpsConfigV4(C.Structure):
+    """upstream ICICLE v4.0.0 VecOpsConfig: the reference's struct (icicle_types.cuh:194-201) + batch_size, columns_batch"""
+    _fields_ = [("stream", C.c_void_p), ("is_a_on_device", C.c_bool), ("is_b_on_device", C.c_bool),
+                ("is_result_on_device", C.c_bool), ("is_async", C.c_bool), ("batch_size", C.c_int),
+                ("columns_batch", C.c_bool), ("ext", C.c_void_p)]
+
+
+def vecops_v4():
+    """lib/upstream_v4/ field library: callbacks read the LONG VecOpsConfig.  The mock forwards `const VecOpsConfig&`
+    (a pointer) untouched, so handing it the upstream struct exercises exactly what a real ICICLE v4 frontend passes,
+    including core/vecops.rs:345-346's batch_size."""
+    import numpy as np
+
+    from midnight_bls12_381_cuda_b200 import _lib as L
+    from oracle import cref as O
+    mock, _ = load(os.path.join(LIBDIR, "upstream_v4"))
+    res = {"mask": mock.mock_registered_mask()}
+    assert C.sizeof(VecOpsConfigV4) == 32 and VecOpsConfigV4.ext.offset == 24 and VecOpsConfigV4.batch_size.offset == 12
+    n, batch = 1 << 10, 5
+    a = O.random_fr(51, n * batch)
+    b = O.random_fr(52, n * batch)
+    s = O.random_fr(53, batch)
+    ptr = L.ptr
+    ok = {}
+    for columns in (False, True):
+        cfg = VecOpsConfigV4(batch_size=batch, columns_batch=columns, ext=0xDEAD0000)     # ext must never be dereferenced
+        for which, op in ((0, 0), (1, 1), (2, 2)):
+            o = np.empty_like(b)
+            rc = mock.mock_vecop(which, ptr(a), ptr(b), C.c_uint64(n), C.byref(cfg), ptr(o))
+            ok[f"vec{which}_{int(columns)}"] = rc == 0 and bool((o == O.vecop(op, a, b)).all())
+        for which, op in ((3, 2), (4, 0)):
+            o = np.empty_like(b)
+            rc = mock.mock_vecop(which, ptr(s), ptr(b), C.c_uint64(n), C.byref(cfg), ptr(o))
+            exp = np.empty_like(b)
+            for k in range(batch):
+                if columns:
+                    exp[k::batch] = O.vecop(op, s[k:k + 1], np.ascontiguousarray(b[k::batch]), a_scalar=True)
+                else:
+                    exp[k * n:(k + 1) * n] = O.vecop(op, s[k:k + 1], b[k * n:(k + 1) * n], a_scalar=True)
+            ok[f"scalar{which}_{int(columns)}"] = rc == 0 and bool((o == exp).all())
+    # batch_size = 0 / 1 behave like the single-vector call
+    cfg = VecOpsConfigV4(batch_size=0)
+    o = np.empty_like(b[:n])
+    rc = mock.mock_vecop(3, ptr(s), ptr(b), C.c_uint64(n), C.byref(cfg), ptr(o))
+    ok["scalar_single"] = rc == 0 and bool((o == O.vecop(2, s[:1], b[:n], a_scalar=True)).all())
+    res["cases"] = ok
+    return res
 
 
 def g2_getters(curve_lib):
@@ -138,4 +187,4 @@ def compute():
 
 
 if __name__ == "__main__":
-    print(json.dumps(registration() if sys.argv[1] == "registration" else compute()))
+    print(json.dumps({"registration": registration, "compute": compute, "vecops_v4": vecops_v4}[sys.argv[1]]()))

@@ -115,3 +115,22 @@ def test_reference_named_flat_vec_ops(cuda, b381, oracle):
     res = np.zeros(4, dtype=np.uint64)
     assert lib.vec_sum_cuda(b381.ptr(res), b381.ptr(da), n, C.byref(cfg)) == 0
     assert fr_ints(res.reshape(1, 4)) == [sum(fr_ints(a)) % P.R_MOD]
+
+
+def test_scalar_vec_batch(cuda, b381, oracle):
+    """b381_scalar_{mul,add}_vec_batch: upstream ICICLE v4 batch semantics (batch_size scalars, batch_size vectors stored
+    as rows or interleaved as columns)"""
+    lib = b381.lib()
+    n, batch = 777, 4
+    b = oracle.random_fr(61, n * batch)
+    s = oracle.random_fr(62, batch)
+    cfg = lib.b381_default_vecops_config()
+    for name, op in (("b381_scalar_mul_vec_batch", 2), ("b381_scalar_add_vec_batch", 0)):
+        for columns in (False, True):
+            out = np.empty_like(b)
+            assert getattr(lib, name)(b381.ptr(s), b381.ptr(b), C.c_uint64(n), batch, columns, C.byref(cfg), b381.ptr(out)) == 0
+            for k in range(batch):
+                got = out[k::batch] if columns else out[k * n:(k + 1) * n]
+                src = np.ascontiguousarray(b[k::batch]) if columns else b[k * n:(k + 1) * n]
+                assert (got == oracle.vecop(op, s[k:k + 1], src, a_scalar=True)).all(), (name, columns, k)
+        assert getattr(lib, name)(b381.ptr(s), b381.ptr(b), C.c_uint64(n), 0, False, C.byref(cfg), b381.ptr(out)) == 11
