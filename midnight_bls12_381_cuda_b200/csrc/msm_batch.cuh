@@ -161,24 +161,53 @@ B381_DI F pair_load_x(uint32_t pos, const uint32_t* svals, const affine_t<F>* pt
 }
 
 // Forward: pre[k*pstride] = product of the denominators before k; returns the product of all B.
+// Software-pipelined three slots deep, because a slot is a chain of three dependent loads (slot word -> sorted entries
+// -> x-coordinates, the last one a random gather at level 0) followed by one 430-instruction product, and ptxas keeps
+// that chain inside the iteration: round 1's loop ran at 42 % of the multiplier pipe with long_scoreboard as top stall.
+// Here iteration k issues the slot word of k+3, the entries of k+2 and the x-gathers of k+1 BEFORE multiplying slot k.
 template <class F, int B, bool L0>
 B381_DI F pair_phase1(const uint32_t* src, size_t sstride, const uint32_t* svals, const affine_t<F>* pts, F* pre,
                       size_t pstride, const xrec_t<F>* xs = nullptr) {
   F acc = one<F>();
-#pragma unroll 4
+  auto slot_word = [&](int k) -> uint32_t { return k < B ? src[(size_t)k * sstride] : (uint32_t)PAIR_NONE; };
+  // PAIR_NONE has the PAIR_SINGLE bit set: neither kind of slot has a denominator
+  auto entries = [&](uint32_t s, uint32_t& i1, uint32_t& i2) {
+    if (s & PAIR_SINGLE) return;
+    if (L0) { i1 = svals[s] >> 1; i2 = svals[s + 1] >> 1; }
+    else { i1 = s; i2 = s + 1; }
+  };
+  auto gather = [&](uint32_t s, uint32_t i1, uint32_t i2, F& x1, F& x2) {
+    if (s & PAIR_SINGLE) return;
+    if (L0 && xs) { x1 = xs[i1].x; x2 = xs[i2].x; }
+    else { x1 = load_wide(&pts[i1].x); x2 = load_wide(&pts[i2].x); }
+  };
+  uint32_t s0 = slot_word(0), s1 = slot_word(1), s2 = slot_word(2);
+  uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0;            // entries of slot k (a) and k+1 (b)
+  F x1 = zero<F>(), x2 = zero<F>(), y1 = zero<F>(), y2 = zero<F>();   // x-coordinates of slot k (x) and k+1 (y)
+  entries(s0, a1, a2);
+  gather(s0, a1, a2, x1, x2);
+  entries(s1, b1, b2);
+#ifndef B381_HOST_TEST
+#pragma unroll 2
+#endif
   for (int k = 0; k < B; k++) {
-    uint32_t s = src[(size_t)k * sstride];
+    const uint32_t s3 = slot_word(k + 3);
+    uint32_t c1 = 0, c2 = 0;
+    entries(s2, c1, c2);                  // slot k+2
+    gather(s1, b1, b2, y1, y2);           // slot k+1
     pre[(size_t)k * pstride] = acc;
-    if (s & PAIR_SINGLE) continue;          // carried-over point or no slot: no denominator
-    F x1 = pair_load_x<F, L0>(s, svals, pts, xs);
-    F x2 = pair_load_x<F, L0>(s + 1, svals, pts, xs);
-    F d = sub(x2, x1);
-    if (is_zero(x1) || is_zero(x2) || is_zero(d)) {   // infinity operand, doubling or cancellation: rare
-      affine_t<F> p = pair_load<F, L0>(s, svals, pts);
-      affine_t<F> q = pair_load<F, L0>(s + 1, svals, pts);
-      pair_classify(p, q, d);
+    if (!(s0 & PAIR_SINGLE)) {
+      F d = sub(x2, x1);
+      if (is_zero(x1) || is_zero(x2) || is_zero(d)) {   // infinity operand, doubling or cancellation: rare
+        affine_t<F> p = pair_load<F, L0>(s0, svals, pts);
+        affine_t<F> q = pair_load<F, L0>(s0 + 1, svals, pts);
+        pair_classify(p, q, d);
+      }
+      acc = mul(acc, d);
     }
-    acc = mul(acc, d);
+    s0 = s1; s1 = s2; s2 = s3;
+    a1 = b1; a2 = b2; b1 = c1; b2 = c2;
+    x1 = y1; x2 = y2;
   }
   return acc;
 }

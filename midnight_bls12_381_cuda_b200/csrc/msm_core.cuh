@@ -29,14 +29,16 @@
 namespace b381 {
 
 struct msm_shape {
-  uint32_t n;        // points in this MSM
+  uint32_t n;        // points per MSM
   uint32_t c;        // window bits
   uint32_t W;        // number of c-bit windows of the scalar
   uint32_t B;        // buckets per window = 2^(c-1)
-  uint32_t Wf;       // bucket sets after folding with precomputed bases: ceil(W / precompute_factor)
+  uint32_t Wf;       // bucket sets per MSM after folding with precomputed bases: ceil(W / precompute_factor)
   uint32_t Bs;       // bucket slots per set = B + 1: slot B of every set is its trash bucket (zero digits)
-  uint32_t nbuckets; // Wf*Bs bucket slots, trash slots included
+  uint32_t nbuckets; // batch*Wf*Bs bucket slots, trash slots included
   uint32_t f;        // precompute_factor (>= 1): point i has f stored multiples, at bases[i*f + k]
+  uint32_t batch;    // MSMs folded into this pipeline run: MSM b owns bucket sets [b*Wf, (b+1)*Wf)
+  uint32_t shared;   // 1: every MSM of the batch reads bases[0 .. n*f); 0: MSM b reads bases[b*n*f ..)
 };
 
 // With precompute_factor f the caller supplies f*n bases, point i's multiples 2^(k*Wf*c) * P_i (k < f) stored
@@ -44,17 +46,25 @@ struct msm_shape {
 // prefix of the same buffer (core/msm.rs:654-661 passes the full buffer whatever scalars.len() is).  Window
 // w = k*Wf + w' is inserted into bucket set w' using multiple k -- all windows of one residue class share buckets,
 // so only Wf bucket sets are reduced and combined.
-B381_HD msm_shape make_msm_shape(uint32_t n, uint32_t c, uint32_t bits, uint32_t factor) {
+// A BATCH of MSMs (MSMConfig.batch_size, core/msm.rs:1179-1295) is one pipeline run over batch*Wf bucket sets: the
+// grouping, the affine levels, the task/accumulate/finalize stages and the bucket reduction never look at which MSM a
+// bucket slot belongs to, so the latency-bound tail (~3 ms) is paid once per batch instead of once per MSM, and small
+// MSMs fill the GPU together.  (The reference loops over the batch on the host, icicle_curve_api.cu:243-407.)
+B381_HD msm_shape make_msm_shape(uint32_t n, uint32_t c, uint32_t bits, uint32_t factor, uint32_t batch = 1,
+                                 bool shared = true) {
   msm_shape sh;
   sh.n = n;
   sh.c = c;
   sh.W = (bits + 1 + c - 1) / c;
   sh.B = 1u << (c - 1);
   if (factor < 1) factor = 1;
+  if (batch < 1) batch = 1;
   sh.Wf = (sh.W + factor - 1) / factor;
   sh.Bs = sh.B + 1;
-  sh.nbuckets = sh.Wf * sh.Bs;
+  sh.nbuckets = batch * sh.Wf * sh.Bs;
   sh.f = factor;
+  sh.batch = batch;
+  sh.shared = shared ? 1u : 0u;
   return sh;
 }
 
@@ -80,8 +90,9 @@ B381_HD uint32_t msm_tasks_of(uint32_t size, uint32_t K) {
 // (msm_kernels.cu:96-130): d in [-(2^(c-1)-1), 2^(c-1)], d > 2^(c-1) => d -= 2^c, carry.
 // Digit w of canonical scalar s: bucket slot `key` = wf*Bs + |d|-1 (zero digits: the set's trash slot wf*Bs + B) and
 // entry `val` = (base index << 1) | sign.  `carry` runs from window 0 upwards.
-B381_DI void msm_digit_at(const fr_t& s, const msm_shape& sh, uint32_t i, uint32_t w, uint32_t& carry, uint32_t& key,
-                          uint32_t& val) {
+// i = index of the scalar within its MSM, b = which MSM of the batch.
+B381_DI void msm_digit_at(const fr_t& s, const msm_shape& sh, uint32_t i, uint32_t b, uint32_t w, uint32_t& carry,
+                          uint32_t& key, uint32_t& val) {
   const uint32_t bit = w * sh.c, limb = bit >> 6, off = bit & 63;
   uint32_t d = 0;
   if (limb < 4) {
@@ -98,8 +109,8 @@ B381_DI void msm_digit_at(const fr_t& s, const msm_shape& sh, uint32_t i, uint32
     carry = 1;
   }
   const uint32_t blk = w / sh.Wf, wf = w - blk * sh.Wf;
-  key = wf * sh.Bs + (d ? d - 1 : sh.B);
-  val = ((i * sh.f + blk) << 1) | sign;
+  key = (b * sh.Wf + wf) * sh.Bs + (d ? d - 1 : sh.B);
+  val = (((sh.shared ? i : b * sh.n + i) * sh.f + blk) << 1) | sign;
   // W*c >= 256 > bit length of any canonical scalar, so the last carry is always 0.
 }
 
@@ -123,22 +134,25 @@ B381_DI uint32_t msm_fetch_add(uint32_t* p, uint32_t v) {
 //   pass 2 (next body)   vals[cursor[key]++] = val                         -- digits recomputed, no key array exists
 // The reference writes 2 x 32-bit keys/values per pair and radix-sorts all 32 key bits with CUB
 // (msm_kernels.cu:69-143, :768-778), then histograms the sorted keys with atomics (:224-256).
-B381_DI void msm_hist_body(uint32_t i, const fr_t* scalars, bool scalars_mont, const msm_shape sh, uint32_t* hist) {
-  if (i >= sh.n) return;
-  fr_t s = scalars[i];
+// t = position in the batch-major scalar array [batch][n]
+B381_DI void msm_hist_body(uint32_t t, const fr_t* scalars, bool scalars_mont, const msm_shape sh, uint32_t* hist) {
+  if (t >= sh.n * sh.batch) return;
+  const uint32_t b = t / sh.n, i = t - b * sh.n;
+  fr_t s = scalars[t];
   if (scalars_mont) s = from_mont(s);
   uint32_t carry = 0, key, val;
   for (uint32_t w = 0; w < sh.W; w++) {
-    msm_digit_at(s, sh, i, w, carry, key, val);
+    msm_digit_at(s, sh, i, b, w, carry, key, val);
     msm_fetch_add(hist + key, 1u);
   }
 }
 
 // pass 2: eight windows at a time so that eight returning atomics, then eight stores, are in flight per thread
-B381_DI void msm_scatter_body(uint32_t i, const fr_t* scalars, bool scalars_mont, const msm_shape sh, uint32_t* cursor,
+B381_DI void msm_scatter_body(uint32_t t, const fr_t* scalars, bool scalars_mont, const msm_shape sh, uint32_t* cursor,
                               uint32_t* vals) {
-  if (i >= sh.n) return;
-  fr_t s = scalars[i];
+  if (t >= sh.n * sh.batch) return;
+  const uint32_t b = t / sh.n, i = t - b * sh.n;
+  fr_t s = scalars[t];
   if (scalars_mont) s = from_mont(s);
   uint32_t carry = 0;
   for (uint32_t w0 = 0; w0 < sh.W; w0 += 8) {
@@ -147,7 +161,7 @@ B381_DI void msm_scatter_body(uint32_t i, const fr_t* scalars, bool scalars_mont
 #pragma unroll
 #endif
     for (uint32_t j = 0; j < 8; j++)
-      if (w0 + j < sh.W) msm_digit_at(s, sh, i, w0 + j, carry, key[j], val[j]);
+      if (w0 + j < sh.W) msm_digit_at(s, sh, i, b, w0 + j, carry, key[j], val[j]);
 #ifndef B381_HOST_TEST
 #pragma unroll
 #endif

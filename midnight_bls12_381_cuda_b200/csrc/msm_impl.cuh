@@ -63,21 +63,25 @@ void launch_msm_finalize(uint32_t nbuckets, const uint32_t* task_start, const ui
                          xyzz_t<F>* buckets, cudaStream_t st);
 
 // Horner over the window sums with four lanes sharing each doubling: msm_tail.cu
+// out[b] = Horner over the W window sums of MSM b (wsum + b*W*stride), one CTA per MSM of the batch
 template <class F>
-void launch_msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c, xyzz_t<F>* out, cudaStream_t st);
+void launch_msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c, xyzz_t<F>* out, uint32_t batch,
+                        cudaStream_t st);
 
 template <class F>
-__global__ void k_msm_set_identity(xyzz_t<F>* out) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) *out = xyzz_identity<F>();
+__global__ void k_msm_set_identity(xyzz_t<F>* out, uint32_t count) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < count) out[i] = xyzz_identity<F>();
 }
 
-// sum `count` XYZZ partials and encode the ICICLE result
+// out[r] = ICICLE encoding of the sum of the `count` XYZZ partials parts[r*count ..], one thread per result
 template <class F>
-__global__ void k_msm_encode(const xyzz_t<F>* parts, int count, bool mont, jacobian_t<F>* out) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+__global__ void k_msm_encode(const xyzz_t<F>* parts, int count, bool mont, jacobian_t<F>* out, uint32_t results) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= results) return;
   xyzz_t<F> acc = xyzz_identity<F>();
-  for (int i = 0; i < count; i++) xyzz_add(acc, parts[i]);
-  *out = msm_result_encode<F>(acc, mont);
+  for (int i = 0; i < count; i++) xyzz_add(acc, parts[(size_t)r * count + i]);
+  out[r] = msm_result_encode<F>(acc, mont);
 }
 
 template <class F>
@@ -208,20 +212,24 @@ static uint32_t pick_window(uint32_t n, uint32_t bits, uint32_t factor, bool g1 
 }
 
 template <class F>
+// `batch` MSMs of n points each in ONE pipeline run (msm_core.cuh make_msm_shape): scalars [batch][n], bases shared or
+// [batch][n * factor], d_out[batch].
 static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const affine_t<F>* d_bases,
-                              uint32_t n, uint32_t c_req, uint32_t bits, uint32_t factor, xyzz_t<F>* d_out) {
+                              uint32_t n, uint32_t c_req, uint32_t bits, uint32_t factor, xyzz_t<F>* d_out,
+                              const fr_t* host_scalars = nullptr, uint32_t batch = 1, bool shared = true) {
   cudaStream_t st = sc.stream();
   if (n == 0) {
-    k_msm_set_identity<F><<<1, 1, 0, st>>>(d_out);
+    k_msm_set_identity<F><<<grid_for(batch, 32), 32, 0, st>>>(d_out, batch);
     return cudaGetLastError();
   }
   PhaseTimer tm(st);
   uint32_t c = c_req ? c_req : pick_window(n, bits, factor, sizeof(F) == sizeof(fq_t));
   if (c < 2) c = 2;
   if (c > 24) c = 24;
-  const msm_shape sh = make_msm_shape(n, c, bits, factor);
-  if ((uint64_t)n * factor >= (1ull << 31)) return cudaErrorInvalidValue;
-  size_t total = (size_t)n * sh.W;
+  const msm_shape sh = make_msm_shape(n, c, bits, factor, batch, shared);
+  const size_t npts = (size_t)n * factor * (shared ? 1u : batch);
+  if (npts >= (1ull << 31) || (uint64_t)sh.Wf * sh.Bs * batch >= (1ull << 31)) return cudaErrorInvalidValue;
+  size_t total = (size_t)n * sh.W * batch;
   if (total >= (1ull << 31)) return cudaErrorInvalidValue;
 
   // -- 1 histogram of the bucket slots, 2 scan = bucket boundaries, 3 scatter (msm_sort.cu; no library sort)
@@ -233,8 +241,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   B381_CUDA_TRY(sc.alloc(&counts, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(sc.alloc(&task_start, (size_t)sh.nbuckets + 1));
   tm.mark("msm:histogram");
-  B381_CUDA_TRY(msm_histogram(sc, d_scalars, scalars_mont, sh, hist));
-  launches++;
+  B381_CUDA_TRY(msm_histogram(sc, d_scalars, scalars_mont, sh, hist, host_scalars, &launches));
   tm.mark("msm:scan+scatter");
   B381_CUDA_TRY(msm_group_pairs(sc, d_scalars, scalars_mont, sh, hist, offsets, vals, &launches));
   const uint32_t* svals = vals;
@@ -291,7 +298,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
         B381_CUDA_TRY(sc.alloc(&tot, nt_max));
       }
       launch_pair_level<F>(l == 0, in_off, out_off, sh.nbuckets, l == 0 ? svals : nullptr,
-                           l == 0 ? d_bases : buf[(l - 1) & 1], (size_t)n * factor, g, srcg, preg, tot, buf[l & 1], st);
+                           l == 0 ? d_bases : buf[(l - 1) & 1], npts, g, srcg, preg, tot, buf[l & 1], st);
       acc_pts = buf[l & 1];
       acc_vals = nullptr;
       in_off = out_off;
@@ -362,11 +369,11 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   while (L > sh.B) L >>= 1;
   uint32_t segs = sh.B / L;
   xyzz_t<F>* seg;
-  B381_CUDA_TRY(sc.alloc(&seg, (size_t)sh.Wf * segs));
-  launch_msm_bucket_reduce<F>(sh.Wf, sh.B, L, buckets, seg, st);
+  B381_CUDA_TRY(sc.alloc(&seg, (size_t)sh.Wf * batch * segs));
+  launch_msm_bucket_reduce<F>(sh.Wf * batch, sh.B, L, buckets, seg, st);
   tm.mark("msm:combine");
   // -- 9 combine
-  launch_msm_combine<F>(seg, segs, sh.Wf, sh.c, d_out, st);
+  launch_msm_combine<F>(seg, segs, sh.Wf, sh.c, d_out, batch, st);
   tm.mark(nullptr);
   {
     int tree = 0;
@@ -403,8 +410,13 @@ static int msm_entry(const fr_t* scalars, const affine_t<F>* bases, int msm_size
     const affine_t<F>* d_bases = nullptr;
     uint32_t factor = cfg->precompute_factor > 1 ? (uint32_t)cfg->precompute_factor : 1u;
     size_t nbases = (cfg->are_points_shared_in_batch ? (size_t)n : (size_t)n * batch) * factor;
-    if ((e = stage_in(sc, scalars, (size_t)n * batch, cfg->are_scalars_on_device, &d_scalars)) != cudaSuccess)
-      return map_cuda_error(e);
+    // host scalars are not staged here: msm_single copies them in chunks under its histogram pass (msm_sort.cu)
+    if (cfg->are_scalars_on_device) d_scalars = scalars;
+    else {
+      fr_t* buf;
+      if ((e = sc.alloc(&buf, (size_t)n * batch)) != cudaSuccess) return map_cuda_error(e);
+      d_scalars = buf;
+    }
     if ((e = stage_in(sc, bases, nbases, cfg->are_points_on_device, &d_bases)) != cudaSuccess)
       return map_cuda_error(e);
     bool bases_mont = cfg->are_points_montgomery_form;
@@ -426,10 +438,27 @@ static int msm_entry(const fr_t* scalars, const affine_t<F>* bases, int msm_size
     }
     xyzz_t<F>* d_part;
     if ((e = sc.alloc(&d_part, (size_t)batch)) != cudaSuccess) return map_cuda_error(e);
-    for (int b = 0; b < batch; b++) {
-      const affine_t<F>* bb = cfg->are_points_shared_in_batch ? d_bases : d_bases + (size_t)b * n * factor;
-      e = msm_single<F>(sc, d_scalars + (size_t)b * n, cfg->are_scalars_montgomery_form, bb, n, (uint32_t)cfg->c,
-                        bits, factor, d_part + b);
+    // The batch runs as few pipeline passes as fit: a group of g MSMs needs g*n*W < 2^31 sorted entries and about
+    // 110 (G1) / 220 (G2) bytes of scratch per entry (entries, two affine level buffers, slot scratch), kept under half
+    // of the memory that is free right now.
+    uint32_t group = (uint32_t)batch;
+    if (n > 0 && batch > 1) {
+      const uint32_t c_eff = cfg->c ? (uint32_t)cfg->c : pick_window(n, bits, factor, sizeof(F) == sizeof(fq_t));
+      const uint64_t per_msm = (uint64_t)n * make_msm_shape(n, c_eff < 2 ? 2 : c_eff, bits, factor).W;
+      size_t free_b = 0, total_b = 0;
+      if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) free_b = (size_t)8 << 30;
+      const uint64_t by_mem = (uint64_t)(free_b / 2) / (per_msm * (sizeof(F) == sizeof(fq_t) ? 110u : 220u) + 1);
+      const uint64_t by_idx = ((1ull << 31) - 1) / (per_msm + 1);
+      uint64_t g = by_mem < by_idx ? by_mem : by_idx;
+      if (const char* ev = getenv("B381_MSM_BATCH_GROUP")) g = (uint64_t)atoi(ev);
+      group = (uint32_t)(g < 1 ? 1 : g > (uint64_t)batch ? (uint64_t)batch : g);
+    }
+    for (uint32_t b0 = 0; b0 < (uint32_t)batch; b0 += group) {
+      const uint32_t g = (uint32_t)batch - b0 < group ? (uint32_t)batch - b0 : group;
+      const bool shared = cfg->are_points_shared_in_batch;
+      const affine_t<F>* bb = shared ? d_bases : d_bases + (size_t)b0 * n * factor;
+      e = msm_single<F>(sc, d_scalars + (size_t)b0 * n, cfg->are_scalars_montgomery_form, bb, n, (uint32_t)cfg->c,
+                        bits, factor, d_part + b0, cfg->are_scalars_on_device ? nullptr : scalars + (size_t)b0 * n, g, shared);
       if (e != cudaSuccess) return map_cuda_error(e);
     }
     if (kind == ResultKind::PartialXyzz) {
@@ -441,8 +470,7 @@ static int msm_entry(const fr_t* scalars, const affine_t<F>* bases, int msm_size
       bool direct = cfg->are_results_on_device;
       if (direct) d_res = reinterpret_cast<jacobian_t<F>*>(results);
       else if ((e = sc.alloc(&d_res, (size_t)batch)) != cudaSuccess) return map_cuda_error(e);
-      for (int b = 0; b < batch; b++)
-        k_msm_encode<F><<<1, 1, 0, st>>>(d_part + b, 1, kind == ResultKind::JacobianMont, d_res + b);
+      k_msm_encode<F><<<grid_for((size_t)batch, 32), 32, 0, st>>>(d_part, 1, kind == ResultKind::JacobianMont, d_res, (uint32_t)batch);
       if (!direct) {
         e = cudaMemcpyAsync(results, d_res, sizeof(jacobian_t<F>) * batch, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) return map_cuda_error(e);
@@ -507,7 +535,7 @@ static int combine_entry(const void* parts, int count, void* stream, bool on_dev
     Scratch sc(st);
     jacobian_t<F>* d_res = reinterpret_cast<jacobian_t<F>*>(result);
     if (!on_device && (e = sc.alloc(&d_res, 1)) != cudaSuccess) return map_cuda_error(e);
-    k_msm_encode<F><<<1, 1, 0, st>>>(reinterpret_cast<const xyzz_t<F>*>(parts), count, false, d_res);
+    k_msm_encode<F><<<1, 32, 0, st>>>(reinterpret_cast<const xyzz_t<F>*>(parts), count, false, d_res, 1u);
     if (!on_device) {
       e = cudaMemcpyAsync(result, d_res, sizeof(jacobian_t<F>), cudaMemcpyDeviceToHost, st);
       if (e != cudaSuccess) return map_cuda_error(e);

@@ -101,8 +101,10 @@ cudaError_t exclusive_scan_u32(Scratch& sc, const uint32_t* in, uint32_t* out, s
 }
 
 // ------------------------------------------------------------------ (bucket, point) pairs: counting sort
-static __global__ void __launch_bounds__(256) k_msm_hist(const fr_t* scalars, bool mont, msm_shape sh, uint32_t* hist) {
-  msm_hist_body(blockIdx.x * blockDim.x + threadIdx.x, scalars, mont, sh, hist);
+static __global__ void __launch_bounds__(256) k_msm_hist(const fr_t* scalars, bool mont, msm_shape sh, uint32_t* hist,
+                                                         uint32_t first, uint32_t end) {
+  const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < end) msm_hist_body(i, scalars, mont, sh, hist);
 }
 
 static __global__ void __launch_bounds__(256) k_msm_scatter(const fr_t* scalars, bool mont, msm_shape sh, uint32_t* cursor,
@@ -110,12 +112,43 @@ static __global__ void __launch_bounds__(256) k_msm_scatter(const fr_t* scalars,
   msm_scatter_body(blockIdx.x * blockDim.x + threadIdx.x, scalars, mont, sh, cursor, vals);
 }
 
-cudaError_t msm_histogram(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, uint32_t* hist) {
+// Host-resident scalars (the plugin call with are_scalars_on_device = false) arrive in chunks on a copy stream and
+// are histogrammed chunk by chunk as they land, so pass 1 rides under the PCIe transfer (2^24 scalars = 512 MiB =
+// 9.4 ms at 57 GB/s; pass 1 = 1.3 ms).  Everything after the histogram needs every scalar.
+cudaError_t msm_histogram(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, uint32_t* hist,
+                          const fr_t* host_src, int* launches) {
   cudaStream_t st = sc.stream();
   // one spare slot: the scan of nbuckets + 1 entries leaves the pair total in offsets[nbuckets]
   B381_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * ((size_t)sh.nbuckets + 1), st));
-  k_msm_hist<<<grid_for(sh.n, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, hist);
-  return cudaGetLastError();
+  constexpr uint32_t kChunk = 1u << 21;                 // 64 MiB of scalars per copy
+  const uint32_t nt = sh.n * sh.batch;                  // scalars of the whole batch, [batch][n]
+  if (!host_src || nt <= kChunk) {
+    if (host_src) B381_CUDA_TRY(cudaMemcpyAsync(const_cast<fr_t*>(d_scalars), host_src, sizeof(fr_t) * nt, cudaMemcpyHostToDevice, st));
+    k_msm_hist<<<grid_for(nt, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, hist, 0u, nt);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+  }
+  cudaStream_t cp;
+  cudaEvent_t ready, landed;
+  B381_CUDA_TRY(cudaStreamCreateWithFlags(&cp, cudaStreamNonBlocking));
+  cudaError_t e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventRecord(ready, st);             // d_scalars is a stream-ordered allocation of `st`
+  if (e == cudaSuccess) e = cudaStreamWaitEvent(cp, ready, 0);
+  if (e == cudaSuccess) cudaEventDestroy(ready);
+  for (uint32_t first = 0; e == cudaSuccess && first < nt; first += kChunk) {
+    const uint32_t end = nt - first < kChunk ? nt : first + kChunk;
+    e = cudaMemcpyAsync(const_cast<fr_t*>(d_scalars) + first, host_src + first, sizeof(fr_t) * (end - first), cudaMemcpyHostToDevice, cp);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&landed, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(landed, cp);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, landed, 0);
+    if (e == cudaSuccess) cudaEventDestroy(landed);                 // released once the recorded work has completed
+    if (e == cudaSuccess) {
+      k_msm_hist<<<grid_for(end - first, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, hist, first, end);
+      if (launches) (*launches)++;
+    }
+  }
+  cudaStreamDestroy(cp);                                            // deferred by the runtime until its copies are done
+  return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t msm_group_pairs(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, const uint32_t* hist,
@@ -124,7 +157,7 @@ cudaError_t msm_group_pairs(Scratch& sc, const fr_t* d_scalars, bool scalars_mon
   uint32_t* cursor;
   B381_CUDA_TRY(sc.alloc(&cursor, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(exclusive_scan_u32(sc, hist, offsets, (size_t)sh.nbuckets + 1, cursor, launches));
-  k_msm_scatter<<<grid_for(sh.n, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, cursor, vals);
+  k_msm_scatter<<<grid_for((size_t)sh.n * sh.batch, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, cursor, vals);
   if (launches) (*launches)++;
   return cudaGetLastError();
 }

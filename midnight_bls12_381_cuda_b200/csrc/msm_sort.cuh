@@ -10,8 +10,11 @@ namespace b381 {
 cudaError_t exclusive_scan_u32(Scratch& sc, const uint32_t* in, uint32_t* out, size_t n, uint32_t* copy = nullptr,
                                int* launches = nullptr);
 
-// pass 1: hist[0..nbuckets] (nbuckets + 1 entries, the last one stays 0) = pairs per bucket slot.  One kernel.
-cudaError_t msm_histogram(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, uint32_t* hist);
+// pass 1: hist[0..nbuckets] (nbuckets + 1 entries, the last one stays 0) = pairs per bucket slot.
+// host_src != nullptr: the scalars are still in (pinned or pageable) HOST memory; they are copied into d_scalars in
+// chunks on a side stream and histogrammed as they land.
+cudaError_t msm_histogram(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, uint32_t* hist,
+                          const fr_t* host_src = nullptr, int* launches = nullptr);
 
 // scan + pass 2: offsets[0..nbuckets] = bucket boundaries (offsets[nbuckets] = n * W), vals[n * W] = entries
 // (base index << 1 | sign) grouped by bucket slot, order inside a bucket unspecified.

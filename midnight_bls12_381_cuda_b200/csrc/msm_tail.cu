@@ -158,12 +158,13 @@ template <class F>
 __global__ void __launch_bounds__(32) k_msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c,
                                                      xyzz_t<F>* out) {
   const int role = threadIdx.x & 3;
+  wsum += (size_t)blockIdx.x * W * stride;            // one CTA per MSM of the batch
   xyzz_t<F> r = xyzz_identity<F>();
   for (int w = (int)W - 1; w >= 0; w--) {
     for (uint32_t k = 0; k < c; k++) r = xyzz_dbl_coop(r, role);
     xyzz_add_coop(r, wsum[(size_t)w * stride], role);
   }
-  if (threadIdx.x == 0) *out = r;
+  if (threadIdx.x == 0) out[blockIdx.x] = r;
 }
 
 // ---- finalize: bucket = sum of its task partials.  One thread per bucket for the usual 0..8 partials,
@@ -214,10 +215,11 @@ template void launch_msm_finalize<fq_t>(uint32_t, const uint32_t*, const uint32_
 template void launch_msm_finalize<fq2_t>(uint32_t, const uint32_t*, const uint32_t*, const xyzz_t<fq2_t>*, xyzz_t<fq2_t>*, cudaStream_t);
 
 template <class F>
-void launch_msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c, xyzz_t<F>* out, cudaStream_t st) {
-  k_msm_combine<F><<<1, 32, 0, st>>>(wsum, stride, W, c, out);
+void launch_msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c, xyzz_t<F>* out, uint32_t batch,
+                        cudaStream_t st) {
+  k_msm_combine<F><<<batch, 32, 0, st>>>(wsum, stride, W, c, out);
 }
-template void launch_msm_combine<fq_t>(const xyzz_t<fq_t>*, uint32_t, uint32_t, uint32_t, xyzz_t<fq_t>*, cudaStream_t);
-template void launch_msm_combine<fq2_t>(const xyzz_t<fq2_t>*, uint32_t, uint32_t, uint32_t, xyzz_t<fq2_t>*, cudaStream_t);
+template void launch_msm_combine<fq_t>(const xyzz_t<fq_t>*, uint32_t, uint32_t, uint32_t, xyzz_t<fq_t>*, uint32_t, cudaStream_t);
+template void launch_msm_combine<fq2_t>(const xyzz_t<fq2_t>*, uint32_t, uint32_t, uint32_t, xyzz_t<fq2_t>*, uint32_t, cudaStream_t);
 
 }  // namespace b381

@@ -12,7 +12,7 @@ import time
 import numpy as np
 
 from . import _lib as L
-from .stream import DeviceVec, ManagedStream, ensure_backend_loaded, set_device
+from .stream import DeviceVec, ManagedStream, PinnedArray, ensure_backend_loaded, set_device
 from .types import G1_AFFINE_BYTES, G1_PROJECTIVE_BYTES, G2_AFFINE_BYTES, G2_PROJECTIVE_BYTES, TypeConverter
 
 
@@ -60,6 +60,8 @@ class _Handle:
         self._stream.synchronize()
         self._stream.destroy()
         self._keep = None
+        if isinstance(self._result, PinnedArray):
+            self._result = self._result.take()
         return self._result
 
 
@@ -77,7 +79,7 @@ class G2MsmHandle(_Handle):
 
 class BatchMsmHandle(_Handle):
     def batch_size(self) -> int:
-        return self._result.shape[0]
+        return self._result.shape[0]          # PinnedArray and ndarray both carry .shape
 
     def wait(self):
         res = self._finish()
@@ -143,9 +145,9 @@ class GpuMsmContext:
         # host scalars go straight into the plugin call: it stages them on THIS call's stream from the stream-ordered
         # pool (no cudaMalloc/cudaFree, no device-wide sync), so two handles in flight overlap copy and compute
         st = ManagedStream.create()
-        res = np.zeros(18, dtype=np.uint64)
+        res = PinnedArray(18)          # pinned: the result copy must not block this thread (see PinnedArray)
         cfg = self._cfg_for(bases, points_on_device=True, stream=st, is_async=True)
-        self._check(L.lib().b381_g1_msm(L.ptr(sc), L.ptr(bases.buffer), sc.shape[0], C.byref(cfg), L.ptr(res)), "msm")
+        self._check(L.lib().b381_g1_msm(L.ptr(sc), L.ptr(bases.buffer), sc.shape[0], C.byref(cfg), L.ptr(res.array)), "msm")
         return MsmHandle(st, res, (sc, bases))
 
     def msm_async(self, scalars, points) -> MsmHandle:
@@ -167,10 +169,10 @@ class GpuMsmContext:
         b, n = sc.shape[0], sc.shape[1]
         bases.required_size_for_scalars(n)
         st = ManagedStream.create()
-        res = np.zeros((b, 18), dtype=np.uint64)
+        res = PinnedArray((b, 18))
         cfg = self._cfg_for(bases, points_on_device=True, stream=st, is_async=True)
         cfg.batch_size, cfg.are_points_shared_in_batch = b, True
-        self._check(L.lib().b381_g1_msm(L.ptr(sc), L.ptr(bases.buffer), n, C.byref(cfg), L.ptr(res)), "msm batch")
+        self._check(L.lib().b381_g1_msm(L.ptr(sc), L.ptr(bases.buffer), n, C.byref(cfg), L.ptr(res.array)), "msm batch")
         return BatchMsmHandle(st, res, (sc, bases))
 
     # -- G2 ------------------------------------------------------------------
@@ -195,9 +197,9 @@ class GpuMsmContext:
         sc = np.ascontiguousarray(TypeConverter.scalar_slice_as_icicle(scalars))
         d_pts = self.upload_g2_bases(points)
         st = ManagedStream.create()
-        res = np.zeros(36, dtype=np.uint64)
+        res = PinnedArray(36)
         cfg = self._cfg(points_on_device=True, stream=st, is_async=True)
-        self._check(L.lib().b381_g2_msm(L.ptr(sc), L.ptr(d_pts), sc.shape[0], C.byref(cfg), L.ptr(res)), "g2 msm")
+        self._check(L.lib().b381_g2_msm(L.ptr(sc), L.ptr(d_pts), sc.shape[0], C.byref(cfg), L.ptr(res.array)), "g2 msm")
         return G2MsmHandle(st, res, (sc, d_pts))
 
     def warmup(self) -> float:

@@ -123,3 +123,37 @@ class DeviceVec:
             self.free()
         except Exception:
             pass
+
+
+class PinnedArray:
+    """uint64 result buffer in page-locked host memory.  An is_async call copies its result device -> host on the
+    call's stream; into pageable memory that copy blocks the calling thread until the whole call has run, into pinned
+    memory it does not -- which is what lets two handles overlap (core/msm.rs:715-798 keeps its results in DeviceVecs
+    for the same reason)."""
+
+    def __init__(self, shape):
+        self.shape = tuple(np.atleast_1d(shape))
+        n = int(np.prod(self.shape))
+        p = C.c_void_p()
+        L.check(L.lib().b381_host_alloc_pinned(C.byref(p), max(8, 8 * n)), "host_alloc_pinned")
+        self._p = p.value
+        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n,)).reshape(self.shape)
+        self.array[...] = 0
+
+    def take(self) -> np.ndarray:
+        """pageable copy of the contents; releases the pinned block"""
+        out = self.array.copy()
+        self.free()
+        return out
+
+    def free(self) -> None:
+        if self._p:
+            self.array = None
+            L.lib().b381_host_free_pinned(C.c_void_p(self._p))
+            self._p = 0
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

@@ -1,7 +1,9 @@
 // CPU-only driver for the per-thread MSM bodies in csrc/msm_core.cuh (TEST INFRASTRUCTURE).
 // Runs exactly the kernel pipeline of csrc/msm_impl.cuh with a serial loop per "kernel" and
 // a serial exclusive scan in place of the device scan.  Usage:
-//   msm_host_sim <g1|g2> <n> <c> <K> <L> <scalars_mont 0|1> <infile> [factor] [levels]; prints result hex (std form)
+//   msm_host_sim <g1|g2> <n> <c> <K> <L> <scalars_mont 0|1> <infile> [factor] [levels] [batch] [shared 0|1]
+// prints one result per MSM of the batch (hex, std form).  batch > 1 folds the MSMs into one pipeline run exactly as
+// msm_impl.cuh does (scalars [batch][n]; points shared or [batch][n]).
 // levels > 0 runs that many affine pre-reduction levels (csrc/msm_batch.cuh) before the tasks, 3 output
 // slots per simulated thread; forward, batched inversion of the thread totals and backward run as the three
 // per-level kernels do.
@@ -17,15 +19,17 @@
 using namespace b381;
 
 template <class F>
-int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint32_t factor, uint32_t levels) {
-  std::vector<fr_t> sc(n);
-  std::vector<affine_t<F>> pts(n);
-  if (fread(sc.data(), sizeof(fr_t), n, f) != n) return 2;
-  if (fread(pts.data(), sizeof(affine_t<F>), n, f) != n) return 2;
-  msm_shape sh = make_msm_shape(n, c, 255, factor);
+int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint32_t factor, uint32_t levels,
+        uint32_t batch, bool shared) {
+  const uint32_t nsc = n * batch, np = shared ? n : n * batch;
+  std::vector<fr_t> sc(nsc);
+  std::vector<affine_t<F>> pts(np);
+  if (fread(sc.data(), sizeof(fr_t), nsc, f) != nsc) return 2;
+  if (fread(pts.data(), sizeof(affine_t<F>), np, f) != np) return 2;
+  msm_shape sh = make_msm_shape(n, c, 255, factor, batch, shared);
   if (factor > 1) {
-    std::vector<affine_t<F>> ex((size_t)n * factor);
-    for (uint32_t i = 0; i < n; i++) {
+    std::vector<affine_t<F>> ex((size_t)np * factor);
+    for (uint32_t i = 0; i < np; i++) {
       ex[(size_t)i * factor] = pts[i];
       xyzz_t<F> acc = to_xyzz(pts[i]);
       for (uint32_t k = 1; k < factor; k++) {
@@ -35,17 +39,17 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint
     }
     pts.swap(ex);
   }
-  size_t total = (size_t)n * sh.W;
+  size_t total = (size_t)nsc * sh.W;
   // counting sort exactly as msm_sort.cu runs it: histogram, exclusive scan, scatter through per-slot cursors.  The
   // "threads" of the scatter pass run in a scrambled order (odd n: descending) because the device gives no ordering
   // guarantee inside a bucket and nothing downstream may depend on one.
   std::vector<uint32_t> hist(sh.nbuckets + 1, 0), offsets(sh.nbuckets + 1, 0xdeadbeef), sv(total, 0xdeadbeef);
-  for (uint32_t i = 0; i < n; i++) msm_hist_body(i, sc.data(), mont, sh, hist.data());
+  for (uint32_t i = 0; i < nsc; i++) msm_hist_body(i, sc.data(), mont, sh, hist.data());
   uint32_t run = 0;
   for (uint32_t b = 0; b <= sh.nbuckets; b++) { offsets[b] = run; run += hist[b]; }
   if (offsets[sh.nbuckets] != total) return 4;
   std::vector<uint32_t> cursor(offsets);
-  for (uint32_t i = 0; i < n; i++) msm_scatter_body((n & 1) ? n - 1 - i : i, sc.data(), mont, sh, cursor.data(), sv.data());
+  for (uint32_t i = 0; i < nsc; i++) msm_scatter_body((n & 1) ? nsc - 1 - i : i, sc.data(), mont, sh, cursor.data(), sv.data());
   for (uint32_t b = 0; b < sh.nbuckets; b++) if (cursor[b] != offsets[b + 1]) return 5;
   // affine pre-reduction levels
   const uint32_t* cur_vals = sv.data();
@@ -92,15 +96,18 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint
   for (uint32_t b = 0; b < sh.nbuckets; b++) msm_finalize_body<F>(b, sh.nbuckets, tstart.data(), counts.data(), partial.data(), buckets.data());
   if (L > sh.B) L = sh.B;
   uint32_t segs = sh.B / L;
-  std::vector<xyzz_t<F>> seg(sh.Wf * segs);
-  for (uint32_t g = 0; g < sh.Wf * segs; g++) msm_segment_body<F>(g, sh.Wf, sh.B, L, buckets.data(), seg.data());
+  const uint32_t WB = sh.Wf * batch;               // bucket sets of the whole batch
+  std::vector<xyzz_t<F>> seg(WB * segs);
+  for (uint32_t g = 0; g < WB * segs; g++) msm_segment_body<F>(g, WB, sh.B, L, buckets.data(), seg.data());
   for (uint32_t half = segs / 2; half >= 1; half /= 2)
-    for (uint32_t g = 0; g < sh.Wf * half; g++) msm_tree_body<F>(g, sh.Wf, segs, half, seg.data());
-  xyzz_t<F> r = msm_combine<F>(seg.data(), segs, sh.Wf, sh.c);
-  jacobian_t<F> o = msm_result_encode<F>(r, false);
-  const unsigned char* p = (const unsigned char*)&o;
-  for (size_t i = 0; i < sizeof(o); i++) printf("%02x", p[i]);
-  printf("\n");
+    for (uint32_t g = 0; g < WB * half; g++) msm_tree_body<F>(g, WB, segs, half, seg.data());
+  for (uint32_t b = 0; b < batch; b++) {
+    xyzz_t<F> r = msm_combine<F>(seg.data() + (size_t)b * sh.Wf * segs, segs, sh.Wf, sh.c);
+    jacobian_t<F> o = msm_result_encode<F>(r, false);
+    const unsigned char* p = (const unsigned char*)&o;
+    for (size_t i = 0; i < sizeof(o); i++) printf("%02x", p[i]);
+    printf("\n");
+  }
   return 0;
 }
 
@@ -113,7 +120,10 @@ int main(int argc, char** argv) {
   if (!f) return 3;
   uint32_t factor = argc > 8 ? atoi(argv[8]) : 1;
   uint32_t levels = argc > 9 ? atoi(argv[9]) : 0;
-  int rc = g2 ? run<fq2_t>(n, c, K, L, mont, f, factor, levels) : run<fq_t>(n, c, K, L, mont, f, factor, levels);
+  uint32_t batch = argc > 10 ? atoi(argv[10]) : 1;
+  bool shared = argc > 11 ? atoi(argv[11]) != 0 : true;
+  int rc = g2 ? run<fq2_t>(n, c, K, L, mont, f, factor, levels, batch, shared)
+              : run<fq_t>(n, c, K, L, mont, f, factor, levels, batch, shared);
   fclose(f);
   return rc;
 }

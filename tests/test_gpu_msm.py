@@ -325,3 +325,38 @@ def test_full_size_discrete_log_check(cuda, b381, oracle):
         d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
         got = raw_msm(b381, group, d_sc, d_bases, n, scalars_on_device=True, points_on_device=True)
         assert got.tobytes() == exp, group
+
+
+def test_batch_is_one_folded_run(cuda, b381, oracle, monkeypatch):
+    """A batch runs as ONE pipeline pass over batch * Wf bucket sets (msm_core.cuh make_msm_shape): results equal the
+    individual MSMs for shared and per-MSM bases, at sizes with and without affine levels, for G2, when the batch has to
+    be cut into groups (B381_MSM_BATCH_GROUP), and with host-resident scalars (chunked copy spans MSM boundaries)."""
+    import torch
+    lib = b381.lib()
+    for (n, b, c) in [(1 << 10, 16, 0), (1 << 16, 6, 16), (3001, 5, 9)]:
+        bases = oracle.gen_series(1, [3, 0, 0, 0], [5, 0, 0, 0], n)
+        sc = oracle.random_fr(500 + n, n * b)
+        singles = [raw_msm(b381, "g1", sc[i * n:(i + 1) * n], bases, n, c=c)[0].tobytes() for i in range(b)]
+        assert singles[0] == oracle.msm(1, sc[:n], bases).tobytes()
+        got = raw_msm(b381, "g1", sc, bases, n, batch=b, c=c)
+        assert [got[i].tobytes() for i in range(b)] == singles, (n, b)
+        monkeypatch.setenv("B381_MSM_BATCH_GROUP", "4")            # 16 -> 4 x 4, 6 -> 4 + 2, 5 -> 4 + 1
+        got = raw_msm(b381, "g1", sc, bases, n, batch=b, c=c)
+        monkeypatch.delenv("B381_MSM_BATCH_GROUP")
+        assert [got[i].tobytes() for i in range(b)] == singles, (n, b, "groups")
+    # per-MSM bases, device-resident inputs
+    n, b = 1 << 12, 7
+    bases_b = oracle.gen_series(1, [2, 0, 0, 0], [9, 0, 0, 0], n * b)
+    sc = oracle.random_fr(77, n * b)
+    singles = [oracle.msm(1, sc[i * n:(i + 1) * n], bases_b[i * n:(i + 1) * n]).tobytes() for i in range(b)]
+    d_sc, d_b = torch.from_numpy(sc.view(np.int64)).cuda(), torch.from_numpy(bases_b.view(np.int64)).cuda()
+    got = raw_msm(b381, "g1", d_sc, d_b, n, batch=b, shared=False, scalars_on_device=True, points_on_device=True)
+    assert [got[i].tobytes() for i in range(b)] == singles
+    # G2
+    n2, b2 = 700, 4
+    bases2 = oracle.gen_series(2, [3, 0, 0, 0], [5, 0, 0, 0], n2)
+    sc2 = oracle.random_fr(78, n2 * b2)
+    got2 = raw_msm(b381, "g2", sc2, bases2, n2, batch=b2)
+    assert [got2[i].tobytes() for i in range(b2)] == [oracle.msm(2, sc2[i * n2:(i + 1) * n2], bases2).tobytes() for i in range(b2)]
+    # empty batch element sizes
+    assert raw_msm(b381, "g1", sc[:0], bases_b[:0], 0, batch=3).tobytes() == P.g1_result_std_bytes(None) * 3

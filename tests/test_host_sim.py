@@ -28,16 +28,37 @@ def sims(tmp_path_factory):
     return bins
 
 
-def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1, levels=0):
+def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1, levels=0, batch=1, shared=True):
+    """batch > 1: `scalars` holds batch * n values ([batch][n]); returns the list of results"""
     path = os.path.join(sims["dir"], "msm_in.bin")
     with open(path, "wb") as f:
         for s in scalars:
             f.write(P.fr_bytes(P.fr_to_mont(s) if mont else s))
         for pt in pts:
             f.write(P.g1_affine_mont_bytes(pt) if group == "g1" else P.g2_affine_mont_bytes(pt))
-    r = subprocess.run([sims["msm_host_sim"], group, str(len(scalars)), str(c), str(K), str(L), str(int(mont)), path,
-                        str(factor), str(levels)], capture_output=True, text=True, check=True)
-    return bytes.fromhex(r.stdout.strip())
+    r = subprocess.run([sims["msm_host_sim"], group, str(len(scalars) // batch), str(c), str(K), str(L), str(int(mont)), path,
+                        str(factor), str(levels), str(batch), str(int(shared))], capture_output=True, text=True, check=True)
+    out = [bytes.fromhex(x) for x in r.stdout.split()]
+    return out[0] if batch == 1 else out
+
+
+def test_msm_batch_folded_into_one_run(sims):
+    """MSMConfig.batch_size: the MSMs of a batch share one pipeline run (bucket sets b*Wf ..), with shared bases and with
+    per-MSM bases, with precomputed-bases folding and with affine levels"""
+    rng = P.SplitMix64(4711)
+    for (n, batch, shared, c, K, L, factor, levels) in [(9, 3, True, 4, 2, 2, 1, 0), (20, 4, False, 5, 3, 4, 1, 2),
+                                                        (33, 2, True, 4, 3, 2, 2, 1), (16, 5, True, 3, 50, 2, 1, 3)]:
+        np_ = n if shared else n * batch
+        ks = [rng.fr() for _ in range(np_)]
+        pts = [P.g1_mul(k, P.G1_GEN) for k in ks]
+        sc = [rng.fr() for _ in range(n * batch)]
+        sc[1], sc[n + 2] = 0, P.R_MOD - 1
+        got = run_msm(sims, "g1", sc, pts, c, K, L, factor=factor, levels=levels, batch=batch, shared=shared)
+        assert len(got) == batch
+        for b in range(batch):
+            kb = ks if shared else ks[b * n:(b + 1) * n]
+            dl = sum(s * k for s, k in zip(sc[b * n:(b + 1) * n], kb)) % P.R_MOD
+            assert got[b] == P.g1_result_std_bytes(P.g1_mul(dl, P.G1_GEN)), (n, batch, shared, b)
 
 
 def test_msm_pipeline_g1(sims):
