@@ -688,7 +688,7 @@ def main():
         fr_rate = v.value
         ms_step = ms_total / args.steps
         ph = [statistics.mean(c) for c in zip(*phases)] if phases else []
-        names = ["histogram", "scan+scatter", "(unused)", "prereduce", "tasks+accumulate", "finalize", "bucket_reduce", "combine"]
+        names = ["sort (histogram+scan+scatter)", "(unused 1)", "(unused 2)", "prereduce", "tasks+accumulate", "finalize", "bucket_reduce", "combine"]
         c_win, W, levels, own_launches = msm_info[0], msm_info[1], msm_info[2], msm_info[3]
         # Dominant stage = bucket accumulation: `levels` affine pre-reduction levels (k_msm_pair_fwd / k_msm_invert_totals /
         # k_msm_pair_bwd, csrc/msm_batch.cuh) + k_msm_accumulate on what is left.  Algorithmic work per (point, window)

@@ -61,17 +61,59 @@ B381_DI T load_wide(const T* p) {
   return *p;
 }
 
+// 128-bit loads of an element that is only 16-byte aligned (a coordinate inside a struct-of-arrays level buffer)
+template <class T>
+B381_DI T load_vec16(const T* p) {
+#if defined(__CUDA_ARCH__) && !defined(B381_NO_WIDE_LD)
+  static_assert(sizeof(T) % 16 == 0, "16-byte granules");
+  T r;
+  uint64_t* w = reinterpret_cast<uint64_t*>(&r);
+  const char* a = reinterpret_cast<const char*>(p);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++)
+    asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(w[2 * i]), "=l"(w[2 * i + 1]) : "l"(a + 16 * i));
+  return r;
+#else
+  return *p;
+#endif
+}
+
+template <class T>
+B381_DI void store_vec16(T* p, const T& v) {
+#if defined(__CUDA_ARCH__) && !defined(B381_NO_WIDE_LD)
+  const uint64_t* w = reinterpret_cast<const uint64_t*>(&v);
+  char* a = reinterpret_cast<char*>(p);
+#pragma unroll
+  for (int i = 0; i < (int)(sizeof(T) / 16); i++)
+    asm volatile("st.global.v2.u64 [%0], {%1, %2};" ::"l"(a + 16 * i), "l"(w[2 * i]), "l"(w[2 * i + 1]) : "memory");
+#else
+  *p = v;
+#endif
+}
+
+// What a level reads.  Level 0 gathers the caller's bases (array of 96/192-byte structs) through the sorted entries;
+// every later level reads the previous level's output, which is kept as TWO arrays (x[], y[]): the forward pass needs
+// the x-coordinates only, and as structs every 48-byte x drags its y through DRAM as well (levels >= 1 of a 2^24-point
+// MSM: 6.7 ms of forward passes at 66 % DRAM).
+template <class F> struct level_pts {
+  const affine_t<F>* aos;   // level 0
+  const F* x;               // levels >= 1
+  const F* y;
+};
+template <class F> B381_HD level_pts<F> level_from_bases(const affine_t<F>* b) { return level_pts<F>{b, nullptr, nullptr}; }
+template <class F> B381_HD level_pts<F> level_from_xy(const F* x, const F* y) { return level_pts<F>{nullptr, x, y}; }
+
 // point at sorted position `pos` of the current level; level 0 gathers through the sorted
 // (index, sign) entries and applies the sign
 template <class F, bool L0>
-B381_DI affine_t<F> pair_load(uint32_t pos, const uint32_t* svals, const affine_t<F>* pts) {
+B381_DI affine_t<F> pair_load(uint32_t pos, const uint32_t* svals, const level_pts<F>& pts) {
   if (L0) {
     uint32_t v = svals[pos];
-    affine_t<F> p = load_wide(pts + (v >> 1));
+    affine_t<F> p = load_wide(pts.aos + (v >> 1));
     if ((v & 1) && !is_inf(p)) p.y = neg(p.y);
     return p;
   }
-  return load_wide(pts + pos);
+  return affine_t<F>{load_vec16(pts.x + pos), load_vec16(pts.y + pos)};
 }
 
 // what P + Q needs, and the denominator that goes into the batched inversion
@@ -112,12 +154,32 @@ B381_DI void msm_half_counts_body(uint32_t b, const uint32_t* offsets, uint32_t 
   counts[b] = (b < nbuckets && b % Bs != Bs - 1) ? (offsets[b + 1] - offsets[b] + 1) / 2 : 0u;
 }
 
+// Chunk-major level 0 (msm_core.cuh): run r = chunk * nbuckets + slot.  Its sums are WRITTEN bucket-major, i.e. in the
+// order (slot, chunk): position perm(r) = slot * nchunks + chunk of the second count array, whose exclusive scan
+// gives every run's first output position -- and, at chunk 0, the level-1 offsets of the bucket slots.
+B381_HD uint32_t msm_run_perm(uint32_t r, uint32_t nbuckets, uint32_t nchunks) {
+  const uint32_t chunk = r / nbuckets, slot = r - chunk * nbuckets;
+  return slot * nchunks + chunk;
+}
+B381_DI void msm_half_counts_runs_body(uint32_t r, const uint32_t* run_off, uint32_t nbuckets, uint32_t nchunks, uint32_t Bs,
+                                       uint32_t* counts, uint32_t* counts_bucket_major) {
+  const uint32_t nruns = nbuckets * nchunks;
+  if (r > nruns) return;
+  if (r == nruns) { counts[r] = 0; counts_bucket_major[r] = 0; return; }
+  const uint32_t h = (r % Bs != Bs - 1) ? (run_off[r + 1] - run_off[r] + 1) / 2 : 0u;   // nbuckets is a multiple of Bs
+  counts[r] = h;
+  counts_bucket_major[msm_run_perm(r, nbuckets, nchunks)] = h;
+}
+
 // slot -> input pair.  src[k*stride] = position of the pair's first point (| PAIR_SINGLE when the bucket's
 // odd last point is just carried over), PAIR_NONE past the end.
+// dst_base != nullptr (chunk-major level 0): "buckets" are runs, and dst[k*stride] = where the slot's sum goes:
+// dst_base[perm(run)] + (slot - first slot of the run).
 template <int B>
 B381_DI void pair_walk(uint32_t slot0, uint32_t n_out, const uint32_t* in_off, const uint32_t* out_off,
-                       uint32_t nbuckets, uint32_t* src, size_t stride) {
-  uint32_t b = 0, ob = 0, oe = 0, ib = 0, ie = 0;
+                       uint32_t nbuckets, uint32_t* src, size_t stride, const uint32_t* dst_base = nullptr,
+                       uint32_t dst_nbuckets = 0, uint32_t dst_nchunks = 0, uint32_t* dst = nullptr) {
+  uint32_t b = 0, ob = 0, oe = 0, ib = 0, ie = 0, db = 0;
   if (slot0 < n_out) {
     // last bucket whose first output slot is <= slot0 (empty buckets share a start with their
     // successor, so "last" is the one that really owns the slot)
@@ -129,8 +191,11 @@ B381_DI void pair_walk(uint32_t slot0, uint32_t n_out, const uint32_t* in_off, c
     b = lo;
     ob = out_off[b]; oe = out_off[b + 1];
     ib = in_off[b]; ie = in_off[b + 1];
+    if (dst_base) db = dst_base[msm_run_perm(b, dst_nbuckets, dst_nchunks)];
   }
+#ifndef B381_HOST_TEST
 #pragma unroll 1
+#endif
   for (int k = 0; k < B; k++) {
     uint32_t j = slot0 + (uint32_t)k;
     uint32_t s = PAIR_NONE;
@@ -138,9 +203,11 @@ B381_DI void pair_walk(uint32_t slot0, uint32_t n_out, const uint32_t* in_off, c
       if (j >= oe) {
         do { b++; ob = oe; oe = out_off[b + 1]; } while (j >= oe);
         ib = in_off[b]; ie = in_off[b + 1];
+        if (dst_base) db = dst_base[msm_run_perm(b, dst_nbuckets, dst_nchunks)];
       }
       s = ib + 2u * (j - ob);
       if (s + 1 >= ie) s |= PAIR_SINGLE;
+      if (dst_base) dst[(size_t)k * stride] = db + (j - ob);
     }
     src[(size_t)k * stride] = s;
   }
@@ -152,12 +219,12 @@ B381_DI void pair_walk(uint32_t slot0, uint32_t n_out, const uint32_t* in_off, c
 template <class F> struct alignas(sizeof(F) <= 64 ? 64 : 128) xrec_t { F x; };
 
 template <class F, bool L0>
-B381_DI F pair_load_x(uint32_t pos, const uint32_t* svals, const affine_t<F>* pts, const xrec_t<F>* xs = nullptr) {
+B381_DI F pair_load_x(uint32_t pos, const uint32_t* svals, const level_pts<F>& pts, const xrec_t<F>* xs = nullptr) {
   if (L0) {
     uint32_t i = svals[pos] >> 1;
-    return xs ? xs[i].x : load_wide(&pts[i].x);
+    return xs ? xs[i].x : load_wide(&pts.aos[i].x);
   }
-  return load_wide(&pts[pos].x);
+  return load_vec16(pts.x + pos);
 }
 
 // Forward: pre[k*pstride] = product of the denominators before k; returns the product of all B.
@@ -166,7 +233,7 @@ B381_DI F pair_load_x(uint32_t pos, const uint32_t* svals, const affine_t<F>* pt
 // that chain inside the iteration: round 1's loop ran at 42 % of the multiplier pipe with long_scoreboard as top stall.
 // Here iteration k issues the slot word of k+3, the entries of k+2 and the x-gathers of k+1 BEFORE multiplying slot k.
 template <class F, int B, bool L0>
-B381_DI F pair_phase1(const uint32_t* src, size_t sstride, const uint32_t* svals, const affine_t<F>* pts, F* pre,
+B381_DI F pair_phase1(const uint32_t* src, size_t sstride, const uint32_t* svals, const level_pts<F>& pts, F* pre,
                       size_t pstride, const xrec_t<F>* xs = nullptr) {
   F acc = one<F>();
   auto slot_word = [&](int k) -> uint32_t { return k < B ? src[(size_t)k * sstride] : (uint32_t)PAIR_NONE; };
@@ -179,7 +246,8 @@ B381_DI F pair_phase1(const uint32_t* src, size_t sstride, const uint32_t* svals
   auto gather = [&](uint32_t s, uint32_t i1, uint32_t i2, F& x1, F& x2) {
     if (s & PAIR_SINGLE) return;
     if (L0 && xs) { x1 = xs[i1].x; x2 = xs[i2].x; }
-    else { x1 = load_wide(&pts[i1].x); x2 = load_wide(&pts[i2].x); }
+    else if (L0) { x1 = load_wide(&pts.aos[i1].x); x2 = load_wide(&pts.aos[i2].x); }
+    else { x1 = load_vec16(pts.x + i1); x2 = load_vec16(pts.x + i2); }
   };
   uint32_t s0 = slot_word(0), s1 = slot_word(1), s2 = slot_word(2);
   uint32_t a1 = 0, a2 = 0, b1 = 0, b2 = 0;            // entries of slot k (a) and k+1 (b)
@@ -212,10 +280,13 @@ B381_DI F pair_phase1(const uint32_t* src, size_t sstride, const uint32_t* svals
   return acc;
 }
 
-// Backward: `inv_total` is the inverse of what phase1 returned; out points at the thread's first slot.
+// Backward: `inv_total` is the inverse of what phase1 returned; outx / outy point at the thread's first slot.
+// dst == nullptr: slot k's sum goes to outx/outy[k] (the caller passes the thread's first slot); else to
+// outx/outy[dst[k*sstride]] (chunk-major level 0: pair_walk).
 template <class F, int B, bool L0>
 B381_DI void pair_phase2(F inv_total, const uint32_t* src, size_t sstride, const uint32_t* svals,
-                         const affine_t<F>* pts, const F* pre, size_t pstride, affine_t<F>* out) {
+                         const level_pts<F>& pts, const F* pre, size_t pstride, F* outx, F* outy,
+                         const uint32_t* dst = nullptr) {
   uint32_t s_next = src[(size_t)(B - 1) * sstride];
 #pragma unroll 1
   for (int k = B - 1; k >= 0; k--) {
@@ -223,14 +294,17 @@ B381_DI void pair_phase2(F inv_total, const uint32_t* src, size_t sstride, const
     if (k) s_next = src[(size_t)(k - 1) * sstride];   // one hop of the src -> svals -> point chain ahead
     if (s == PAIR_NONE) continue;
     uint32_t p0 = s & ~PAIR_SINGLE;
+    const size_t o = dst ? (size_t)dst[(size_t)k * sstride] : (size_t)k;
     affine_t<F> p = pair_load<F, L0>(p0, svals, pts);
-    if (s & PAIR_SINGLE) { out[k] = p; continue; }
+    if (s & PAIR_SINGLE) { store_vec16(outx + o, p.x); store_vec16(outy + o, p.y); continue; }
     affine_t<F> q = pair_load<F, L0>(p0 + 1, svals, pts);
     F d;
     int kind = pair_classify(p, q, d);
     F dinv = mul(inv_total, pre[(size_t)k * pstride]);
     if (k) inv_total = mul(inv_total, d);
-    out[k] = pair_finish(kind, p, q, dinv);
+    const affine_t<F> r = pair_finish(kind, p, q, dinv);
+    store_vec16(outx + o, r.x);
+    store_vec16(outy + o, r.y);
   }
 }
 

@@ -32,16 +32,26 @@ static __global__ void k_msm_build_tasks(const uint32_t* offsets, const uint32_t
 
 template <class F, int MINB = 1>
 __global__ void __launch_bounds__(128, MINB) k_msm_accumulate(const uint32_t* ntasks_dev, const uint2* tasks,
-                                                              const uint32_t* sorted_vals, const affine_t<F>* bases,
+                                                              const uint32_t* sorted_vals, const level_pts<F> pts,
                                                               xyzz_t<F>* partial, const uint32_t* order) {
   uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-  msm_accumulate_body<F>(t, *ntasks_dev, tasks, sorted_vals, bases, partial, order);
+  msm_accumulate_body<F>(t, *ntasks_dev, tasks, sorted_vals, pts, partial, order);
 }
 
 // ---- affine pre-reduction (msm_batch.cuh): three kernels per level, no barriers ----------------
 static __global__ void k_msm_half_counts(const uint32_t* offsets, uint32_t nbuckets, uint32_t Bs, uint32_t* counts) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   msm_half_counts_body(b, offsets, nbuckets, Bs, counts);
+}
+
+static __global__ void k_msm_half_counts_runs(const uint32_t* run_off, uint32_t nbuckets, uint32_t nchunks, uint32_t Bs,
+                                              uint32_t* counts, uint32_t* counts_bucket_major) {
+  msm_half_counts_runs_body(blockIdx.x * blockDim.x + threadIdx.x, run_off, nbuckets, nchunks, Bs, counts, counts_bucket_major);
+}
+// bucket slot k's level-1 entries start where its chunk-0 run's sums were written
+static __global__ void k_msm_level1_offsets(const uint32_t* dst_base, uint32_t nbuckets, uint32_t nchunks, uint32_t* off1) {
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k <= nbuckets) off1[k] = dst_base[(size_t)k * nchunks];
 }
 
 // The three kernels of a level live in msm_pair.cu (their own translation unit: seconds to compile).
@@ -51,18 +61,18 @@ static __global__ void k_msm_half_counts(const uint32_t* offsets, uint32_t nbuck
 int msm_pair_levels(double avg, size_t total);
 template <class F>
 void launch_pair_level(bool level0, const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets,
-                       const uint32_t* svals, const affine_t<F>* pts, size_t npts, unsigned grid, uint32_t* srcg, F* preg,
-                       F* tot, affine_t<F>* out, cudaStream_t st);
+                       const uint32_t* svals, const level_pts<F> pts, size_t npts, unsigned grid, uint32_t* srcg, F* preg,
+                       F* tot, F* outx, F* outy, cudaStream_t st, const uint32_t* dst_base = nullptr,
+                       uint32_t dst_nbuckets = 0, uint32_t dst_nchunks = 0, uint32_t* dst_slots = nullptr);
 
 // window sums from the buckets, four lanes per segment: msm_tail.cu
 template <class F>
 void launch_msm_bucket_reduce(uint32_t W, uint32_t B, uint32_t L, const xyzz_t<F>* buckets, xyzz_t<F>* seg, cudaStream_t st);
-// bucket = sum of its task partials (thread per bucket, warp per heavy bucket): msm_tail.cu
+// bucket = sum of its task partials (thread per bucket, warp per listed heavy bucket): msm_tail.cu
 template <class F>
 void launch_msm_finalize(uint32_t nbuckets, const uint32_t* task_start, const uint32_t* counts, const xyzz_t<F>* partial,
-                         xyzz_t<F>* buckets, cudaStream_t st);
+                         xyzz_t<F>* buckets, uint32_t* heavy_list, uint32_t* heavy_count, cudaStream_t st);
 
-// Horner over the window sums with four lanes sharing each doubling: msm_tail.cu
 // out[b] = Horner over the W window sums of MSM b (wsum + b*W*stride), one CTA per MSM of the batch
 template <class F>
 void launch_msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c, xyzz_t<F>* out, uint32_t batch,
@@ -226,56 +236,77 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   uint32_t c = c_req ? c_req : pick_window(n, bits, factor, sizeof(F) == sizeof(fq_t));
   if (c < 2) c = 2;
   if (c > 24) c = 24;
-  const msm_shape sh = make_msm_shape(n, c, bits, factor, batch, shared);
+  msm_shape sh = make_msm_shape(n, c, bits, factor, batch, shared);
   const size_t npts = (size_t)n * factor * (shared ? 1u : batch);
   if (npts >= (1ull << 31) || (uint64_t)sh.Wf * sh.Bs * batch >= (1ull << 31)) return cudaErrorInvalidValue;
   size_t total = (size_t)n * sh.W * batch;
   if (total >= (1ull << 31)) return cudaErrorInvalidValue;
 
-  // -- 1 histogram of the bucket slots, 2 scan = bucket boundaries, 3 scatter (msm_sort.cu; no library sort)
+  // how many affine levels will run (a level pays once there are enough pairs to fill the GPU and buckets are still long)
+  double avg = (double)n * sh.W / ((double)sh.Wf * sh.B);   // mean bucket load seen by the accumulate kernel
+  int levels = msm_pair_levels(avg, total);
+  {
+    const char* e = getenv("B381_MSM_LEVELS");
+    if (e && e[0]) levels = atoi(e);
+    if (levels > 16) levels = 16;
+  }
+  // chunk-major grouping (msm_core.cuh) when level 0 runs and the bases are several times larger than the L2 can hold:
+  // chunks of 100 MB of bases (2^20 G1 / 2^19 G2 points), from 8 chunks up, at most 64.  Measured on B200
+  // (profiles/r02d_msm_chunk_sweep.txt): 2^24 points 77.5 -> 74.3 ms (level-0 forward pass 10.7 -> 7.0 ms), 2^23
+  // 40.7 -> 39.6; chunks of 2^19 / 2^18 are slower (shorter runs: more carried-over singles), 2^22 points gain nothing.
+  {
+    const bool g1 = sizeof(F) == sizeof(fq_t);
+    uint32_t chunk_log = g1 ? 20u : 19u;
+    const uint64_t nt = (uint64_t)n * batch;
+    bool worth = levels >= 1 && nt >= (8ull << chunk_log);
+    if (const char* e = getenv("B381_MSM_CHUNK_LOG")) {          // A/B runs and tests: any size, 31 = off
+      chunk_log = (uint32_t)atoi(e);
+      worth = levels >= 1 && chunk_log < 31 && nt > (1ull << chunk_log);
+    }
+    while (chunk_log < 31 && ((nt + (1ull << chunk_log) - 1) >> chunk_log) > 64) chunk_log++;
+    if (worth) msm_shape_set_chunks(sh, chunk_log);
+    if ((uint64_t)msm_runs(sh) >= (1ull << 31)) msm_shape_set_chunks(sh, 31);
+  }
+  const size_t nruns = msm_runs(sh);
+
+  // -- 1 histogram of the runs, 2 scan = run boundaries, 3 scatter (msm_sort.cu; no library sort)
   int launches = 0;
-  uint32_t *vals, *hist, *offsets, *counts, *task_start;
+  uint32_t *vals, *hist, *run_off, *offsets, *counts, *task_start;
   B381_CUDA_TRY(sc.alloc(&vals, total));
-  B381_CUDA_TRY(sc.alloc(&hist, (size_t)sh.nbuckets + 1));
-  B381_CUDA_TRY(sc.alloc(&offsets, (size_t)sh.nbuckets + 1));
+  B381_CUDA_TRY(sc.alloc(&hist, nruns + 1));
+  B381_CUDA_TRY(sc.alloc(&run_off, nruns + 1));
   B381_CUDA_TRY(sc.alloc(&counts, (size_t)sh.nbuckets + 1));
   B381_CUDA_TRY(sc.alloc(&task_start, (size_t)sh.nbuckets + 1));
-  tm.mark("msm:histogram");
-  B381_CUDA_TRY(msm_histogram(sc, d_scalars, scalars_mont, sh, hist, host_scalars, &launches));
-  tm.mark("msm:scan+scatter");
-  B381_CUDA_TRY(msm_group_pairs(sc, d_scalars, scalars_mont, sh, hist, offsets, vals, &launches));
+  if (sh.nchunks > 1) B381_CUDA_TRY(sc.alloc(&offsets, (size_t)sh.nbuckets + 1));
+  else offsets = run_off;                       // one chunk: runs ARE bucket slots
+  tm.mark("msm:sort");
+  B381_CUDA_TRY(msm_sort_pairs(sc, d_scalars, scalars_mont, sh, host_scalars, hist, run_off, vals, &launches));
   const uint32_t* svals = vals;
   tm.mark(nullptr);
-  tm.mark("msm:affine_levels");     // (phase slot kept: "offsets" was a separate pass over the sorted keys in round 1)
+  tm.mark(nullptr);     // (two phase slots kept: histogram / scatter / offsets were separately timed passes before)
+  tm.mark("msm:affine_levels");
 
   // -- 3b affine pre-reduction levels (msm_batch.cuh): each halves every bucket
-  const affine_t<F>* acc_pts = d_bases;
+  level_pts<F> acc_pts = level_from_bases(d_bases);
   const uint32_t* acc_vals = svals;
   int n_levels = 0;
-  double avg = (double)n * sh.W / ((double)sh.Wf * sh.B);   // mean bucket load seen by the accumulate kernel
   {
-    // a level pays once there are enough pairs to fill the GPU and buckets are still long
-    int levels = 0;
-    {
-      levels = msm_pair_levels(avg, total);
-      const char* e = getenv("B381_MSM_LEVELS");
-      if (e && e[0]) levels = atoi(e);
-      if (levels > 16) levels = 16;
-    }
     size_t max_in = total;
-    const uint32_t* in_off = offsets;
-    affine_t<F>* buf[2] = {nullptr, nullptr};
+    const uint32_t* in_off = run_off;
+    F* bufx[2] = {nullptr, nullptr};              // ping-pong level outputs, struct of arrays (msm_batch.cuh level_pts)
+    F* bufy[2] = {nullptr, nullptr};
     constexpr int PB = pair_batch<F>::B;
-    uint32_t* srcg = nullptr;
+    uint32_t *srcg = nullptr, *dstg = nullptr;
     F *preg = nullptr, *tot = nullptr;
     // The slot-major scratch (stride nt = grid * PR_TPB) and the ping-pong point buffers are allocated once, for the
     // LARGEST level.  That is level 0 while total > nbuckets + 2, but the bound (in + nbuckets) / 2 + 1 GROWS from level
     // to level on a sparse input (forced B381_MSM_LEVELS with few points per bucket), so take the maximum over the plan.
+    // (Level 0 of a chunk-major run rounds up once per RUN, not once per bucket slot.)
     size_t nt_max = 0, nt_buf[2] = {0, 0};        // scratch stride; point buffers of the even / odd levels
     {
       size_t in = total;
       for (int l = 0; l < levels; l++) {
-        const size_t out = (in + sh.nbuckets) / 2 + 1;
+        const size_t out = (in + (l == 0 ? nruns : (size_t)sh.nbuckets)) / 2 + 1;
         const size_t nt_l = (size_t)grid_for(out, (size_t)PR_TPB * PB) * PR_TPB;
         if (nt_l > nt_max) nt_max = nt_l;
         if (nt_l > nt_buf[l & 1]) nt_buf[l & 1] = nt_l;
@@ -283,25 +314,49 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
       }
     }
     for (int l = 0; l < levels; l++) {
-      const size_t max_out = (max_in + sh.nbuckets) / 2 + 1;
-      uint32_t *half, *out_off;
-      B381_CUDA_TRY(sc.alloc(&half, (size_t)sh.nbuckets + 1));
-      B381_CUDA_TRY(sc.alloc(&out_off, (size_t)sh.nbuckets + 1));
-      k_msm_half_counts<<<grid_for((size_t)sh.nbuckets + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, sh.Bs, half);
-      B381_CUDA_TRY(exclusive_scan_u32(sc, half, out_off, (size_t)sh.nbuckets + 1, nullptr, &launches));
+      const bool chunked = l == 0 && sh.nchunks > 1;
+      const size_t nb_l = chunked ? nruns : (size_t)sh.nbuckets;        // "buckets" of this level
+      const size_t max_out = (max_in + nb_l) / 2 + 1;
+      uint32_t *half, *out_off, *dst_base = nullptr;
+      B381_CUDA_TRY(sc.alloc(&half, nb_l + 1));
+      B381_CUDA_TRY(sc.alloc(&out_off, nb_l + 1));
+      if (chunked) {
+        // sums are produced run by run (chunk-major) and WRITTEN bucket-major: second count array in (slot, chunk) order
+        uint32_t* half_bm;
+        B381_CUDA_TRY(sc.alloc(&half_bm, nb_l + 1));
+        B381_CUDA_TRY(sc.alloc(&dst_base, nb_l + 1));
+        k_msm_half_counts_runs<<<grid_for(nb_l + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, sh.nchunks, sh.Bs, half, half_bm);
+        B381_CUDA_TRY(exclusive_scan_u32(sc, half_bm, dst_base, nb_l + 1, nullptr, &launches));
+      } else {
+        k_msm_half_counts<<<grid_for(nb_l + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, sh.Bs, half);
+      }
+      B381_CUDA_TRY(exclusive_scan_u32(sc, half, out_off, nb_l + 1, nullptr, &launches));
       launches += 4;      // half counts + forward, invert, backward
       const unsigned g = grid_for(max_out, (size_t)PR_TPB * PB);
-      if (!buf[l & 1]) B381_CUDA_TRY(sc.alloc(&buf[l & 1], nt_buf[l & 1] * PB));   // ping-pong
+      if (!bufx[l & 1]) {
+        B381_CUDA_TRY(sc.alloc(&bufx[l & 1], nt_buf[l & 1] * PB));
+        B381_CUDA_TRY(sc.alloc(&bufy[l & 1], nt_buf[l & 1] * PB));
+      }
       if (!srcg) {
         B381_CUDA_TRY(sc.alloc(&srcg, nt_max * PB));
         B381_CUDA_TRY(sc.alloc(&preg, nt_max * PB));
         B381_CUDA_TRY(sc.alloc(&tot, nt_max));
+        if (sh.nchunks > 1) B381_CUDA_TRY(sc.alloc(&dstg, nt_max * PB));
       }
-      launch_pair_level<F>(l == 0, in_off, out_off, sh.nbuckets, l == 0 ? svals : nullptr,
-                           l == 0 ? d_bases : buf[(l - 1) & 1], npts, g, srcg, preg, tot, buf[l & 1], st);
-      acc_pts = buf[l & 1];
+      launch_pair_level<F>(l == 0, in_off, out_off, (uint32_t)nb_l, l == 0 ? svals : nullptr, acc_pts, npts, g, srcg, preg,
+                           tot, bufx[l & 1], bufy[l & 1], st, dst_base, sh.nbuckets, sh.nchunks, dstg);
+      acc_pts = level_from_xy<F>(bufx[l & 1], bufy[l & 1]);
       acc_vals = nullptr;
-      in_off = out_off;
+      if (chunked) {
+        // from here on nothing knows about chunks: bucket slot k's entries are the sums of its runs, chunk after chunk
+        uint32_t* off1;
+        B381_CUDA_TRY(sc.alloc(&off1, (size_t)sh.nbuckets + 1));
+        k_msm_level1_offsets<<<grid_for((size_t)sh.nbuckets + 1, 256), 256, 0, st>>>(dst_base, sh.nbuckets, sh.nchunks, off1);
+        launches++;
+        in_off = off1;
+      } else {
+        in_off = out_off;
+      }
       max_in = max_out;
       avg *= 0.5;
     }
@@ -354,7 +409,11 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   }
   tm.mark("msm:finalize");
   // -- 6 finalize
-  launch_msm_finalize<F>(sh.nbuckets, task_start, counts, partial, buckets, st);
+  {
+    uint32_t* heavy;           // [0] = count, [1 ..] = list
+    B381_CUDA_TRY(sc.alloc(&heavy, (size_t)sh.nbuckets + 1));
+    launch_msm_finalize<F>(sh.nbuckets, task_start, counts, partial, buckets, heavy + 1, heavy, st);
+  }
   tm.mark("msm:bucket_reduce");
 
   // -- 7 segments, 8 tree

@@ -9,15 +9,19 @@
 namespace b381 {
 
 // thread t owns output slots [t*B, t*B + B); nt = threads in the grid = stride of the slot-major scratch
+// chunk-major level 0 (msm_core.cuh): "buckets" are runs and dst_base / dstg carry where each slot's sum is written
+struct pair_dst { const uint32_t* base; uint32_t nbuckets, nchunks; uint32_t* slots; };
+
 template <class F, int B, bool L0>
 __global__ void __launch_bounds__(PR_TPB, 4) k_msm_pair_fwd(const uint32_t* in_off, const uint32_t* out_off,
                                                             uint32_t nbuckets, const uint32_t* svals,
-                                                            const affine_t<F>* pts, uint32_t nt, uint32_t* srcg,
-                                                            F* preg, F* tot, const xrec_t<F>* xs) {
+                                                            const level_pts<F> pts, uint32_t nt, uint32_t* srcg,
+                                                            F* preg, F* tot, const xrec_t<F>* xs, const pair_dst dst) {
   const uint32_t n_out = out_off[nbuckets];
   const uint32_t t = blockIdx.x * PR_TPB + threadIdx.x;
   if ((uint64_t)t * B >= n_out) return;
-  pair_walk<B>(t * B, n_out, in_off, out_off, nbuckets, srcg + t, nt);
+  pair_walk<B>(t * B, n_out, in_off, out_off, nbuckets, srcg + t, nt, dst.base, dst.nbuckets, dst.nchunks,
+               dst.base ? dst.slots + t : nullptr);
   tot[t] = pair_phase1<F, B, L0>(srcg + t, nt, svals, pts, preg + t, nt, xs);
 }
 
@@ -39,13 +43,14 @@ __global__ void __launch_bounds__(128) k_msm_invert_totals(const uint32_t* out_o
 
 template <class F, int B, bool L0, int MINB>
 __global__ void __launch_bounds__(PR_TPB, MINB) k_msm_pair_bwd(const uint32_t* out_off, uint32_t nbuckets,
-                                                               const uint32_t* svals, const affine_t<F>* pts,
+                                                               const uint32_t* svals, const level_pts<F> pts,
                                                                uint32_t nt, const uint32_t* srcg, const F* preg,
-                                                               const F* tot, affine_t<F>* out) {
+                                                               const F* tot, F* outx, F* outy, const uint32_t* dstg) {
   const uint32_t n_out = out_off[nbuckets];
   const uint32_t t = blockIdx.x * PR_TPB + threadIdx.x;
   if ((uint64_t)t * B >= n_out) return;
-  pair_phase2<F, B, L0>(tot[t], srcg + t, nt, svals, pts, preg + t, nt, out + (size_t)t * B);
+  if (dstg) pair_phase2<F, B, L0>(tot[t], srcg + t, nt, svals, pts, preg + t, nt, outx, outy, dstg + t);
+  else pair_phase2<F, B, L0>(tot[t], srcg + t, nt, svals, pts, preg + t, nt, outx + (size_t)t * B, outy + (size_t)t * B);
 }
 
 // Live timing of the dominant kernels (level-0 forward and backward pass) for bench.py's roofline, recorded on
@@ -63,8 +68,8 @@ static bool l0_timing_on() {
 
 template <class F, bool L0>
 static void launch_level(const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets, const uint32_t* svals,
-                         const affine_t<F>* pts, size_t npts, unsigned g, uint32_t* srcg, F* preg, F* tot, affine_t<F>* out,
-                         cudaStream_t st) {
+                         const level_pts<F> pts, size_t npts, unsigned g, uint32_t* srcg, F* preg, F* tot, F* outx, F* outy,
+                         const pair_dst dst, cudaStream_t st) {
   constexpr int PB = pair_batch<F>::B, PM = pair_batch<F>::M;
   const uint32_t nt = g * PR_TPB;
   const unsigned gi = (unsigned)((((size_t)nt + 3) / 4 + 127) / 128);   // enough for the smallest per-thread batch (4)
@@ -78,19 +83,19 @@ static void launch_level(const uint32_t* in_off, const uint32_t* out_off, uint32
   // but building the copy costs 0.5 ms -- no net gain, so it is off by default.
   static const int xpack = [] { const char* e = getenv("B381_XPACK"); return e ? atoi(e) : 0; }();
   if (L0 && xpack && npts >= ((size_t)1 << 20) && cudaMallocAsync(&xs, npts * sizeof(xrec_t<F>), st) == cudaSuccess)
-    k_pack_x<F><<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(pts, npts, xs);
+    k_pack_x<F><<<(unsigned)((npts + 255) / 256), 256, 0, st>>>(pts.aos, npts, xs);
   else
     xs = nullptr;
   const bool timed = L0 && sizeof(F) == sizeof(fq_t) && l0_timing_on();
   if (timed) cudaEventRecord(g_l0_ev[0], st);
-  k_msm_pair_fwd<F, PB, L0><<<g, PR_TPB, 0, st>>>(in_off, out_off, nbuckets, svals, pts, nt, srcg, preg, tot, xs);
+  k_msm_pair_fwd<F, PB, L0><<<g, PR_TPB, 0, st>>>(in_off, out_off, nbuckets, svals, pts, nt, srcg, preg, tot, xs, dst);
   if (timed) cudaEventRecord(g_l0_ev[1], st);
   if (xs) cudaFreeAsync(xs, st);
   k_msm_invert_totals<F, PB, PM><<<gi, 128, 0, st>>>(out_off, nbuckets, tot);
   if (timed) cudaEventRecord(g_l0_ev[2], st);
-  if (mb == 2) k_msm_pair_bwd<F, PB, L0, 2><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
-  else if (mb == 3) k_msm_pair_bwd<F, PB, L0, 3><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
-  else k_msm_pair_bwd<F, PB, L0, 4><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, out);
+  if (mb == 2) k_msm_pair_bwd<F, PB, L0, 2><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, outx, outy, dst.base ? dst.slots : nullptr);
+  else if (mb == 3) k_msm_pair_bwd<F, PB, L0, 3><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, outx, outy, dst.base ? dst.slots : nullptr);
+  else k_msm_pair_bwd<F, PB, L0, 4><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, outx, outy, dst.base ? dst.slots : nullptr);
   if (timed) {
     cudaEventRecord(g_l0_ev[3], st);
     g_l0_ev_valid = true;
@@ -109,16 +114,20 @@ int msm_pair_levels(double avg, size_t total) {
 
 template <class F>
 void launch_pair_level(bool level0, const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets,
-                       const uint32_t* svals, const affine_t<F>* pts, size_t npts, unsigned grid, uint32_t* srcg, F* preg,
-                       F* tot, affine_t<F>* out, cudaStream_t st) {
-  if (level0) launch_level<F, true>(in_off, out_off, nbuckets, svals, pts, npts, grid, srcg, preg, tot, out, st);
-  else launch_level<F, false>(in_off, out_off, nbuckets, nullptr, pts, npts, grid, srcg, preg, tot, out, st);
+                       const uint32_t* svals, const level_pts<F> pts, size_t npts, unsigned grid, uint32_t* srcg, F* preg,
+                       F* tot, F* outx, F* outy, cudaStream_t st, const uint32_t* dst_base, uint32_t dst_nbuckets,
+                       uint32_t dst_nchunks, uint32_t* dst_slots) {
+  const pair_dst dst{dst_base, dst_nbuckets, dst_nchunks, dst_slots};
+  if (level0) launch_level<F, true>(in_off, out_off, nbuckets, svals, pts, npts, grid, srcg, preg, tot, outx, outy, dst, st);
+  else launch_level<F, false>(in_off, out_off, nbuckets, nullptr, pts, npts, grid, srcg, preg, tot, outx, outy, dst, st);
 }
 
-template void launch_pair_level<fq_t>(bool, const uint32_t*, const uint32_t*, uint32_t, const uint32_t*, const affine_t<fq_t>*,
-                                      size_t, unsigned, uint32_t*, fq_t*, fq_t*, affine_t<fq_t>*, cudaStream_t);
-template void launch_pair_level<fq2_t>(bool, const uint32_t*, const uint32_t*, uint32_t, const uint32_t*, const affine_t<fq2_t>*,
-                                       size_t, unsigned, uint32_t*, fq2_t*, fq2_t*, affine_t<fq2_t>*, cudaStream_t);
+template void launch_pair_level<fq_t>(bool, const uint32_t*, const uint32_t*, uint32_t, const uint32_t*, const level_pts<fq_t>,
+                                      size_t, unsigned, uint32_t*, fq_t*, fq_t*, fq_t*, fq_t*, cudaStream_t, const uint32_t*,
+                                      uint32_t, uint32_t, uint32_t*);
+template void launch_pair_level<fq2_t>(bool, const uint32_t*, const uint32_t*, uint32_t, const uint32_t*, const level_pts<fq2_t>,
+                                       size_t, unsigned, uint32_t*, fq2_t*, fq2_t*, fq2_t*, fq2_t*, cudaStream_t, const uint32_t*,
+                                       uint32_t, uint32_t, uint32_t*);
 
 }  // namespace b381
 

@@ -17,7 +17,8 @@ namespace b381 {
 // short launches beat a decoupled look-back single pass on latency.
 constexpr int SCAN_TPB = 256, SCAN_IPT = 16, SCAN_TILE = SCAN_TPB * SCAN_IPT;
 
-static __global__ void __launch_bounds__(SCAN_TPB) k_scan_tile(const uint32_t* in, uint32_t* out, size_t n, uint32_t* tile_sums) {
+static __global__ void __launch_bounds__(SCAN_TPB) k_scan_tile(const uint32_t* in, uint32_t* out, size_t n, uint32_t* tile_sums,
+                                                               uint32_t add) {
   __shared__ uint32_t warp_tot[SCAN_TPB / 32];
   const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_IPT;
   uint32_t v[SCAN_IPT];
@@ -44,7 +45,7 @@ static __global__ void __launch_bounds__(SCAN_TPB) k_scan_tile(const uint32_t* i
   }
   if (lane == 31) warp_tot[wid] = incl;
   __syncthreads();
-  uint32_t pre = incl - sum;                       // exclusive prefix of this thread inside its warp
+  uint32_t pre = add + incl - sum;                // exclusive prefix of this thread inside its warp (+ the caller's base)
   uint32_t tile_total = 0;
 #pragma unroll
   for (int w = 0; w < SCAN_TPB / 32; w++) {
@@ -64,10 +65,11 @@ static __global__ void __launch_bounds__(SCAN_TPB) k_scan_tile(const uint32_t* i
   if (tile_sums && threadIdx.x == 0) tile_sums[blockIdx.x] = tile_total;
 }
 
-static __global__ void __launch_bounds__(256) k_scan_add(uint32_t* out, size_t n, const uint32_t* tile_offs, uint32_t* copy) {
+static __global__ void __launch_bounds__(256) k_scan_add(uint32_t* out, size_t n, const uint32_t* tile_offs, uint32_t* copy,
+                                                         uint32_t base) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t v = out[i] + tile_offs[i / SCAN_TILE];
+  const uint32_t v = out[i] + tile_offs[i / SCAN_TILE] + base;
   out[i] = v;
   if (copy) copy[i] = v;
 }
@@ -77,12 +79,13 @@ static __global__ void __launch_bounds__(256) k_copy_u32(const uint32_t* in, uin
   if (i < n) out[i] = in[i];
 }
 
-cudaError_t exclusive_scan_u32(Scratch& sc, const uint32_t* in, uint32_t* out, size_t n, uint32_t* copy, int* launches) {
+cudaError_t exclusive_scan_u32(Scratch& sc, const uint32_t* in, uint32_t* out, size_t n, uint32_t* copy, int* launches,
+                               uint32_t base) {
   if (n == 0) return cudaSuccess;
   cudaStream_t st = sc.stream();
   const size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (tiles == 1) {
-    k_scan_tile<<<1, SCAN_TPB, 0, st>>>(in, out, n, nullptr);
+    k_scan_tile<<<1, SCAN_TPB, 0, st>>>(in, out, n, nullptr, base);
     if (launches) (*launches)++;
     if (copy) {
       k_copy_u32<<<grid_for(n, 256), 256, 0, st>>>(out, copy, n);
@@ -92,10 +95,10 @@ cudaError_t exclusive_scan_u32(Scratch& sc, const uint32_t* in, uint32_t* out, s
   }
   uint32_t* sums;
   B381_CUDA_TRY(sc.alloc(&sums, tiles));
-  k_scan_tile<<<(unsigned)tiles, SCAN_TPB, 0, st>>>(in, out, n, sums);
+  k_scan_tile<<<(unsigned)tiles, SCAN_TPB, 0, st>>>(in, out, n, sums, 0u);
   if (launches) (*launches)++;
-  B381_CUDA_TRY(exclusive_scan_u32(sc, sums, sums, tiles, nullptr, launches));
-  k_scan_add<<<grid_for(n, 256), 256, 0, st>>>(out, n, sums, copy);
+  B381_CUDA_TRY(exclusive_scan_u32(sc, sums, sums, tiles, nullptr, launches, 0u));
+  k_scan_add<<<grid_for(n, 256), 256, 0, st>>>(out, n, sums, copy, base);
   if (launches) (*launches)++;
   return cudaGetLastError();
 }
@@ -103,29 +106,39 @@ cudaError_t exclusive_scan_u32(Scratch& sc, const uint32_t* in, uint32_t* out, s
 // ------------------------------------------------------------------ (bucket, point) pairs: counting sort
 static __global__ void __launch_bounds__(256) k_msm_hist(const fr_t* scalars, bool mont, msm_shape sh, uint32_t* hist,
                                                          uint32_t first, uint32_t end) {
-  const uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < end) msm_hist_body(i, scalars, mont, sh, hist);
+  const uint32_t t = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < end) msm_hist_body(t, scalars, mont, sh, hist);
 }
 
 static __global__ void __launch_bounds__(256) k_msm_scatter(const fr_t* scalars, bool mont, msm_shape sh, uint32_t* cursor,
-                                                            uint32_t* vals) {
-  msm_scatter_body(blockIdx.x * blockDim.x + threadIdx.x, scalars, mont, sh, cursor, vals);
+                                                            uint32_t* vals, uint32_t first, uint32_t end) {
+  const uint32_t t = first + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < end) msm_scatter_body(t, scalars, mont, sh, cursor, vals);
 }
 
-// Host-resident scalars (the plugin call with are_scalars_on_device = false) arrive in chunks on a copy stream and
-// are histogrammed chunk by chunk as they land, so pass 1 rides under the PCIe transfer (2^24 scalars = 512 MiB =
-// 9.4 ms at 57 GB/s; pass 1 = 1.3 ms).  Everything after the histogram needs every scalar.
-cudaError_t msm_histogram(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, uint32_t* hist,
-                          const fr_t* host_src, int* launches) {
+// hist: msm_runs(sh) + 1 words of scratch; run_off: msm_runs(sh) + 1 words, the result.
+// Resident scalars: one histogram kernel, one scan, one scatter kernel.
+// Host scalars (host_src != nullptr; the plugin call with are_scalars_on_device = false): they cross PCIe in pieces on
+// a copy stream (2^24 scalars = 512 MiB = 9.4 ms at 57 GB/s) and every piece is histogrammed as it lands; when the
+// grouping is chunk-major a piece is a whole number of chunks, each chunk owns a fixed region of the sorted array,
+// and the piece is scanned and scattered right away too, so the entire sort rides under the transfer.
+cudaError_t msm_sort_pairs(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, const fr_t* host_src,
+                           uint32_t* hist, uint32_t* run_off, uint32_t* vals, int* launches) {
   cudaStream_t st = sc.stream();
-  // one spare slot: the scan of nbuckets + 1 entries leaves the pair total in offsets[nbuckets]
-  B381_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * ((size_t)sh.nbuckets + 1), st));
-  constexpr uint32_t kChunk = 1u << 21;                 // 64 MiB of scalars per copy
   const uint32_t nt = sh.n * sh.batch;                  // scalars of the whole batch, [batch][n]
-  if (!host_src || nt <= kChunk) {
+  const size_t nruns = msm_runs(sh);
+  uint32_t* cursor;
+  B381_CUDA_TRY(sc.alloc(&cursor, nruns + 1));
+  // one spare slot: the scan of nruns + 1 entries leaves the pair total in run_off[nruns]
+  B381_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (nruns + 1), st));
+  uint32_t piece = 1u << 21;                            // 64 MiB of scalars per copy
+  if (sh.nchunks > 1 && sh.chunk_log > 21) piece = 1u << sh.chunk_log;
+  if (!host_src || nt <= piece) {
     if (host_src) B381_CUDA_TRY(cudaMemcpyAsync(const_cast<fr_t*>(d_scalars), host_src, sizeof(fr_t) * nt, cudaMemcpyHostToDevice, st));
     k_msm_hist<<<grid_for(nt, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, hist, 0u, nt);
-    if (launches) (*launches)++;
+    B381_CUDA_TRY(exclusive_scan_u32(sc, hist, run_off, nruns + 1, cursor, launches, 0u));
+    k_msm_scatter<<<grid_for(nt, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, cursor, vals, 0u, nt);
+    if (launches) *launches += 2;
     return cudaGetLastError();
   }
   cudaStream_t cp;
@@ -135,30 +148,33 @@ cudaError_t msm_histogram(Scratch& sc, const fr_t* d_scalars, bool scalars_mont,
   if (e == cudaSuccess) e = cudaEventRecord(ready, st);             // d_scalars is a stream-ordered allocation of `st`
   if (e == cudaSuccess) e = cudaStreamWaitEvent(cp, ready, 0);
   if (e == cudaSuccess) cudaEventDestroy(ready);
-  for (uint32_t first = 0; e == cudaSuccess && first < nt; first += kChunk) {
-    const uint32_t end = nt - first < kChunk ? nt : first + kChunk;
+  const bool per_piece = sh.nchunks > 1;                            // chunks are self-contained: sort piece by piece
+  for (uint32_t first = 0; e == cudaSuccess && first < nt; first += piece) {
+    const uint32_t end = nt - first < piece ? nt : first + piece;
     e = cudaMemcpyAsync(const_cast<fr_t*>(d_scalars) + first, host_src + first, sizeof(fr_t) * (end - first), cudaMemcpyHostToDevice, cp);
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&landed, cudaEventDisableTiming);
     if (e == cudaSuccess) e = cudaEventRecord(landed, cp);
     if (e == cudaSuccess) e = cudaStreamWaitEvent(st, landed, 0);
     if (e == cudaSuccess) cudaEventDestroy(landed);                 // released once the recorded work has completed
-    if (e == cudaSuccess) {
-      k_msm_hist<<<grid_for(end - first, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, hist, first, end);
+    if (e != cudaSuccess) break;
+    k_msm_hist<<<grid_for(end - first, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, hist, first, end);
+    if (launches) (*launches)++;
+    if (per_piece) {
+      const size_t r0 = (size_t)(first >> sh.chunk_log) * sh.nbuckets;
+      const size_t r1 = end == nt ? nruns + 1 : (size_t)(end >> sh.chunk_log) * sh.nbuckets;   // last piece: + the total slot
+      e = exclusive_scan_u32(sc, hist + r0, run_off + r0, r1 - r0, cursor + r0, launches, first * sh.W);
+      if (e != cudaSuccess) break;
+      k_msm_scatter<<<grid_for(end - first, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, cursor, vals, first, end);
       if (launches) (*launches)++;
     }
   }
   cudaStreamDestroy(cp);                                            // deferred by the runtime until its copies are done
-  return e != cudaSuccess ? e : cudaGetLastError();
-}
-
-cudaError_t msm_group_pairs(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, const uint32_t* hist,
-                            uint32_t* offsets, uint32_t* vals, int* launches) {
-  cudaStream_t st = sc.stream();
-  uint32_t* cursor;
-  B381_CUDA_TRY(sc.alloc(&cursor, (size_t)sh.nbuckets + 1));
-  B381_CUDA_TRY(exclusive_scan_u32(sc, hist, offsets, (size_t)sh.nbuckets + 1, cursor, launches));
-  k_msm_scatter<<<grid_for((size_t)sh.n * sh.batch, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, cursor, vals);
-  if (launches) (*launches)++;
+  if (e != cudaSuccess) return e;
+  if (!per_piece) {
+    B381_CUDA_TRY(exclusive_scan_u32(sc, hist, run_off, nruns + 1, cursor, launches, 0u));
+    k_msm_scatter<<<grid_for(nt, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, cursor, vals, 0u, nt);
+    if (launches) (*launches)++;
+  }
   return cudaGetLastError();
 }
 
@@ -219,7 +235,7 @@ cudaError_t msm_task_order(Scratch& sc, size_t max_tasks, const uint32_t* ntasks
   B381_CUDA_TRY(sc.alloc(&hist, bins));
   B381_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * bins, st));
   k_msm_task_hist<<<grid_for(max_tasks, 256), 256, 0, st>>>(ntasks_dev, tasks, K, hist, use_smem);
-  B381_CUDA_TRY(exclusive_scan_u32(sc, hist, hist, bins, nullptr, launches));
+  B381_CUDA_TRY(exclusive_scan_u32(sc, hist, hist, bins, nullptr, launches, 0u));
   k_msm_task_scatter<<<grid_for(max_tasks, 256), 256, 0, st>>>(ntasks_dev, tasks, K, hist, order, use_smem);
   if (launches) *launches += 2;
   return cudaGetLastError();

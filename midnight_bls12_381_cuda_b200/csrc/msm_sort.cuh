@@ -5,21 +5,18 @@
 
 namespace b381 {
 
-// out[i] = sum of in[0..i) for i < n (in == out allowed); `copy`, when given, receives the same values (the scatter
-// cursors).  `launches` counts the kernels launched.
+// out[i] = base + sum of in[0..i) for i < n (in == out allowed); `copy`, when given, receives the same values (the
+// scatter cursors).  `launches` counts the kernels launched.
 cudaError_t exclusive_scan_u32(Scratch& sc, const uint32_t* in, uint32_t* out, size_t n, uint32_t* copy = nullptr,
-                               int* launches = nullptr);
+                               int* launches = nullptr, uint32_t base = 0);
 
-// pass 1: hist[0..nbuckets] (nbuckets + 1 entries, the last one stays 0) = pairs per bucket slot.
-// host_src != nullptr: the scalars are still in (pinned or pageable) HOST memory; they are copied into d_scalars in
-// chunks on a side stream and histogrammed as they land.
-cudaError_t msm_histogram(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, uint32_t* hist,
-                          const fr_t* host_src = nullptr, int* launches = nullptr);
-
-// scan + pass 2: offsets[0..nbuckets] = bucket boundaries (offsets[nbuckets] = n * W), vals[n * W] = entries
-// (base index << 1 | sign) grouped by bucket slot, order inside a bucket unspecified.
-cudaError_t msm_group_pairs(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, const uint32_t* hist,
-                            uint32_t* offsets, uint32_t* vals, int* launches = nullptr);
+// Counting sort of the (run, point) pairs (run = chunk * nbuckets + bucket slot, msm_core.cuh): histogram, scan, scatter.
+// hist: msm_runs(sh) + 1 words of scratch.  run_off[0 .. msm_runs(sh)] = run boundaries (last = n * W * batch),
+// vals[n * W * batch] = entries (base index << 1 | sign) grouped by run, order inside a run unspecified.
+// host_src != nullptr: the scalars are still in HOST memory; they are copied into d_scalars in pieces on a side stream
+// and sorted as they land.
+cudaError_t msm_sort_pairs(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, const fr_t* host_src,
+                           uint32_t* hist, uint32_t* run_off, uint32_t* vals, int* launches = nullptr);
 
 // order[0..ntasks) = task ids, longest task first (ties in unspecified order); K = task length bound
 cudaError_t msm_task_order(Scratch& sc, size_t max_tasks, const uint32_t* ntasks_dev, const uint2* tasks, uint32_t K,

@@ -167,13 +167,16 @@ __global__ void __launch_bounds__(32) k_msm_combine(const xyzz_t<F>* wsum, uint3
   if (threadIdx.x == 0) out[blockIdx.x] = r;
 }
 
-// ---- finalize: bucket = sum of its task partials.  One thread per bucket for the usual 0..8 partials,
-// one warp per bucket for the heavy ones (skewed scalar distributions; at most kMaxTasksPerBucket).
+// ---- finalize: bucket = sum of its task partials.  One thread per bucket for the usual 0..8 partials; buckets with
+// more (skewed scalar distributions; at most kMaxTasksPerBucket) are appended to a list and summed by one warp each.
+// The list keeps the second kernel's grid small: as a warp-per-bucket launch over ALL buckets it spent 0.28 ms of a
+// 2^24-point MSM scheduling 131 k CTAs that found nothing to do (profiles/r01d_launches_summary.txt).
 template <class F>
 __global__ void __launch_bounds__(128) k_msm_finalize(uint32_t nbuckets, const uint32_t* task_start,
                                                       const uint32_t* counts, const xyzz_t<F>* partial,
-                                                      xyzz_t<F>* buckets) {
+                                                      xyzz_t<F>* buckets, uint32_t* heavy_list, uint32_t* heavy_count) {
   uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < nbuckets && counts[b] > kFinalizeSerialMax) heavy_list[atomicAdd(heavy_count, 1u)] = b;
   msm_finalize_body<F>(b, nbuckets, task_start, counts, partial, buckets, kFinalizeSerialMax);
 }
 
@@ -187,32 +190,37 @@ __device__ __forceinline__ xyzz_t<F> shfl_down_point(const xyzz_t<F>& v, int off
   return r;
 }
 
-template <class F>
-__global__ void __launch_bounds__(128) k_msm_finalize_heavy(uint32_t nbuckets, const uint32_t* task_start,
-                                                            const uint32_t* counts, const xyzz_t<F>* partial,
-                                                            xyzz_t<F>* buckets) {
-  const uint32_t b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (b >= nbuckets) return;
-  const uint32_t nt = counts[b];
-  if (nt <= kFinalizeSerialMax) return;
-  const uint32_t t0 = task_start[b];
-  xyzz_t<F> acc = xyzz_identity<F>();
-  for (uint32_t t = lane; t < nt; t += 32) xyzz_add(acc, partial[t0 + t]);
-  for (int off = 16; off >= 1; off >>= 1) {
-    xyzz_t<F> o = shfl_down_point(acc, off);
-    xyzz_add(acc, o);
-  }
-  if (lane == 0) buckets[b] = acc;
-}
+constexpr unsigned kHeavyGrid = 148 * 4;       // warps loop over the list
 
 template <class F>
-void launch_msm_finalize(uint32_t nbuckets, const uint32_t* task_start, const uint32_t* counts, const xyzz_t<F>* partial,
-                         xyzz_t<F>* buckets, cudaStream_t st) {
-  k_msm_finalize<F><<<grid_for(nbuckets, 128), 128, 0, st>>>(nbuckets, task_start, counts, partial, buckets);
-  k_msm_finalize_heavy<F><<<grid_for((size_t)nbuckets * 32, 128), 128, 0, st>>>(nbuckets, task_start, counts, partial, buckets);
+__global__ void __launch_bounds__(128) k_msm_finalize_heavy(const uint32_t* heavy_list, const uint32_t* heavy_count,
+                                                            const uint32_t* task_start, const uint32_t* counts,
+                                                            const xyzz_t<F>* partial, xyzz_t<F>* buckets) {
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t nwarps = (gridDim.x * blockDim.x) >> 5, total = *heavy_count;
+  for (uint32_t i = warp; i < total; i += nwarps) {
+    const uint32_t b = heavy_list[i];
+    const uint32_t nt = counts[b], t0 = task_start[b];
+    xyzz_t<F> acc = xyzz_identity<F>();
+    for (uint32_t t = lane; t < nt; t += 32) xyzz_add(acc, partial[t0 + t]);
+    for (int off = 16; off >= 1; off >>= 1) {
+      xyzz_t<F> o = shfl_down_point(acc, off);
+      xyzz_add(acc, o);
+    }
+    if (lane == 0) buckets[b] = acc;
+  }
 }
-template void launch_msm_finalize<fq_t>(uint32_t, const uint32_t*, const uint32_t*, const xyzz_t<fq_t>*, xyzz_t<fq_t>*, cudaStream_t);
-template void launch_msm_finalize<fq2_t>(uint32_t, const uint32_t*, const uint32_t*, const xyzz_t<fq2_t>*, xyzz_t<fq2_t>*, cudaStream_t);
+
+// heavy_list: nbuckets entries of scratch; heavy_count: one zeroed word
+template <class F>
+void launch_msm_finalize(uint32_t nbuckets, const uint32_t* task_start, const uint32_t* counts, const xyzz_t<F>* partial,
+                         xyzz_t<F>* buckets, uint32_t* heavy_list, uint32_t* heavy_count, cudaStream_t st) {
+  cudaMemsetAsync(heavy_count, 0, sizeof(uint32_t), st);
+  k_msm_finalize<F><<<grid_for(nbuckets, 128), 128, 0, st>>>(nbuckets, task_start, counts, partial, buckets, heavy_list, heavy_count);
+  k_msm_finalize_heavy<F><<<kHeavyGrid, 128, 0, st>>>(heavy_list, heavy_count, task_start, counts, partial, buckets);
+}
+template void launch_msm_finalize<fq_t>(uint32_t, const uint32_t*, const uint32_t*, const xyzz_t<fq_t>*, xyzz_t<fq_t>*, uint32_t*, uint32_t*, cudaStream_t);
+template void launch_msm_finalize<fq2_t>(uint32_t, const uint32_t*, const uint32_t*, const xyzz_t<fq2_t>*, xyzz_t<fq2_t>*, uint32_t*, uint32_t*, cudaStream_t);
 
 template <class F>
 void launch_msm_combine(const xyzz_t<F>* wsum, uint32_t stride, uint32_t W, uint32_t c, xyzz_t<F>* out, uint32_t batch,

@@ -360,3 +360,50 @@ def test_batch_is_one_folded_run(cuda, b381, oracle, monkeypatch):
     assert [got2[i].tobytes() for i in range(b2)] == [oracle.msm(2, sc2[i * n2:(i + 1) * n2], bases2).tobytes() for i in range(b2)]
     # empty batch element sizes
     assert raw_msm(b381, "g1", sc[:0], bases_b[:0], 0, batch=3).tobytes() == P.g1_result_std_bytes(None) * 3
+
+
+@pytest.mark.parametrize("chunk_log", ["13", "15"])
+def test_chunk_major_grouping(cuda, b381, oracle, monkeypatch, chunk_log):
+    """msm_core.cuh CHUNK-MAJOR GROUPING (default from 2^23 points; forced here at 2^16-2^17 with small chunks): same bytes
+    as the plain grouping and as the oracle; resident and host scalars (per-piece sort under the copy), batch, G2."""
+    import torch
+    monkeypatch.setenv("B381_MSM_LEVELS", "2")
+    n = (1 << 16) + 777
+    bases = oracle.gen_series(1, [3, 0, 0, 0], [5, 0, 0, 0], n)
+    sc = oracle.random_fr(31, n)
+    sc[5], sc[6] = 0, sc[7]
+    exp = oracle.msm(1, sc, bases).tobytes()
+    monkeypatch.setenv("B381_MSM_CHUNK_LOG", "31")
+    assert raw_msm(b381, "g1", sc, bases, n, c=10)[0].tobytes() == exp
+    monkeypatch.setenv("B381_MSM_CHUNK_LOG", chunk_log)
+    assert raw_msm(b381, "g1", sc, bases, n, c=10)[0].tobytes() == exp                         # host scalars
+    d_sc, d_b = torch.from_numpy(sc.view(np.int64)).cuda(), torch.from_numpy(bases.view(np.int64)).cuda()
+    assert raw_msm(b381, "g1", d_sc, d_b, n, c=10, scalars_on_device=True, points_on_device=True)[0].tobytes() == exp
+    # batch of 3 over shared bases; chunks straddle the MSM boundaries
+    nb = 20000
+    scb = oracle.random_fr(32, nb * 3)
+    got = raw_msm(b381, "g1", scb, bases[:nb], nb, batch=3, c=9)
+    assert [g.tobytes() for g in got] == [oracle.msm(1, scb[i * nb:(i + 1) * nb], bases[:nb]).tobytes() for i in range(3)]
+    # G2
+    n2 = 9000
+    bases2 = oracle.gen_series(2, [3, 0, 0, 0], [5, 0, 0, 0], n2)
+    sc2 = oracle.random_fr(33, n2)
+    assert raw_msm(b381, "g2", sc2, bases2, n2, c=8)[0].tobytes() == oracle.msm(2, sc2, bases2).tobytes()
+
+
+def test_chunk_major_host_scalars_large(cuda, b381, oracle, monkeypatch):
+    """2^22 host scalars in two 2^21 pieces, chunk-major with 2^20 chunks: every piece is histogrammed, scanned and
+    scattered while the next one is still in flight; checked against the discrete-log identity."""
+    import torch
+    monkeypatch.setenv("B381_MSM_CHUNK_LOG", "20")
+    lib = b381.lib()
+    n = 1 << 22
+    g = np.frombuffer(P.g1_affine_mont_bytes(P.G1_GEN), dtype=np.uint64).copy()
+    bases = torch.empty((n, 12), dtype=torch.int64, device="cuda")
+    assert lib.b381_g1_point_series(b381.ptr(g), b381.ptr(g), C.c_uint64(n), b381.ptr(bases), None) == 0
+    sc = oracle.random_fr(34, n)
+    got = raw_msm(b381, "g1", sc, bases, n, points_on_device=True)[0].tobytes()
+    kk = np.zeros((n, 4), dtype=np.uint64)
+    kk[:, 0] = np.arange(1, n + 1, dtype=np.uint64)
+    dl = P.from_limbs(oracle.fr_dot(sc, kk))
+    assert got == P.g1_result_std_bytes(P.g1_mul(dl, P.G1_GEN))

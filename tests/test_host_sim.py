@@ -28,7 +28,7 @@ def sims(tmp_path_factory):
     return bins
 
 
-def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1, levels=0, batch=1, shared=True):
+def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1, levels=0, batch=1, shared=True, chunk_log=31):
     """batch > 1: `scalars` holds batch * n values ([batch][n]); returns the list of results"""
     path = os.path.join(sims["dir"], "msm_in.bin")
     with open(path, "wb") as f:
@@ -37,9 +37,39 @@ def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1, levels=0, b
         for pt in pts:
             f.write(P.g1_affine_mont_bytes(pt) if group == "g1" else P.g2_affine_mont_bytes(pt))
     r = subprocess.run([sims["msm_host_sim"], group, str(len(scalars) // batch), str(c), str(K), str(L), str(int(mont)), path,
-                        str(factor), str(levels), str(batch), str(int(shared))], capture_output=True, text=True, check=True)
+                        str(factor), str(levels), str(batch), str(int(shared)), str(chunk_log)],
+                       capture_output=True, text=True, check=True)
     out = [bytes.fromhex(x) for x in r.stdout.split()]
     return out[0] if batch == 1 else out
+
+
+def test_msm_chunk_major_grouping(sims, tmp_path):
+    """msm_core.cuh CHUNK-MAJOR GROUPING: entries grouped by (chunk of scalars, bucket slot), level 0 pairs inside runs
+    and writes its sums bucket-major; same result as the plain grouping, G1 and G2, batch, folding, exceptional pairs
+    (repeated bases, P - P, infinity), chunk sizes that do not divide n -- also once under ASan + UBSan."""
+    exe = str(tmp_path / "msm_host_sim_asan")
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-D_GLIBCXX_ASSERTIONS", f"-I{HOST}",
+                    f"-I{CSRC}", "-o", exe, os.path.join(HOST, "msm_host_sim.cpp")], check=True)
+    asan = dict(sims)
+    asan["msm_host_sim"] = exe
+    rng = P.SplitMix64(1919)
+    for (group, n, batch, c, K, L, factor, levels, chunk_log, which) in [
+            ("g1", 70, 1, 4, 3, 4, 1, 3, 4, sims), ("g1", 64, 1, 3, 50, 2, 1, 1, 3, sims), ("g1", 45, 3, 4, 3, 2, 2, 2, 5, sims),
+            ("g1", 90, 1, 3, 4, 2, 1, 6, 4, asan), ("g2", 20, 2, 4, 3, 4, 1, 2, 3, asan)]:
+        mul, gen = (P.g1_mul, P.G1_GEN) if group == "g1" else (P.g2_mul, P.G2_GEN)
+        ks = [rng.fr() for _ in range(n)]
+        pts = [mul(k, gen) for k in ks]
+        pts[5], ks[5] = None, 0
+        pts[7], ks[7] = pts[6], ks[6]                              # P + P inside a run
+        pts[9], ks[9] = (P.g1_neg(pts[8]) if group == "g1" else P.g2_neg(pts[8])), P.R_MOD - ks[8]
+        sc = [rng.fr() for _ in range(n * batch)]
+        sc[1], sc[2], sc[7], sc[9] = 0, sc[3], sc[6], sc[8]
+        got = run_msm(which, group, sc, pts, c, K, L, factor=factor, levels=levels, batch=batch, chunk_log=chunk_log)
+        got = [got] if batch == 1 else got
+        for b in range(batch):
+            dl = sum(s * k for s, k in zip(sc[b * n:(b + 1) * n], ks)) % P.R_MOD
+            exp = P.g1_result_std_bytes(mul(dl, gen)) if group == "g1" else P.g2_result_std_bytes(mul(dl, gen))
+            assert got[b] == exp, (group, n, batch, chunk_log, b)
 
 
 def test_msm_batch_folded_into_one_run(sims):
