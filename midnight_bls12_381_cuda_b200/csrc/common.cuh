@@ -47,6 +47,11 @@ inline void configure_pool_once() {
   if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    // Never satisfy an allocation on stream B out of memory whose free is still pending on stream A by making B WAIT
+    // for A: two calls in flight on two streams (the async handles of the host API) would run one after the other.
+    // With 180 GB the pool simply grows to the working set of both.
+    int off = 0;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolReuseAllowInternalDependencies, &off);
   }
   done[dev] = true;
 }

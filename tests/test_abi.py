@@ -63,3 +63,29 @@ def test_no_cpu_fallback_in_product():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 txt = open(os.path.join(d, f), errors="ignore").read()
                 assert "oracle" not in txt.replace("oracle/pyref.py, which derives", ""), os.path.join(d, f)
+
+
+def test_rust_ffi_names_exist_in_the_library(b381):
+    """rust/src/ffi.rs cannot be compiled here (no Rust toolchain): at least every symbol it declares must be exported
+    by libb381_cuda.so, and its config structs must list the fields of include/b381.h in the same order."""
+    import re
+    src = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    names = re.findall(r"pub fn (b381_\w+|bls12_381_\w+)\(", src)
+    assert len(names) >= 35
+    lib = b381.lib()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    hdr = open(os.path.join(ROOT, "include", "b381.h")).read()
+
+    def c_fields(struct):
+        body = re.search(r"typedef struct[^{]*\{([^}]*)\}\s*" + struct + ";", hdr).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        return [re.split(r"[\s\*]+", d.strip())[-1] for d in body.split(";") if d.strip()]
+
+    def rust_fields(struct):
+        body = re.search(r"pub struct " + struct + r"\s*\{([^}]*)\}", src).group(1)
+        return re.findall(r"pub (\w+):", body)
+
+    for c_name, r_name in (("b381_msm_config", "MsmConfig"), ("b381_ntt_config", "NttConfig"),
+                           ("b381_vecops_config", "VecOpsConfig"), ("b381_ntt_init_domain_config", "NttInitDomainConfig")):
+        assert c_fields(c_name) == rust_fields(r_name), (c_name, c_fields(c_name), rust_fields(r_name))
