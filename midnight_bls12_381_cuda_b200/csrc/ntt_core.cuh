@@ -83,30 +83,44 @@ struct ntt_tile {
 };
 B381_HD uint32_t ntt_tile_slot(uint32_t pos) { return pos ^ ((pos >> 3) & 7u); }
 
+// the 16-byte halves travel as two 64-bit words (ulonglong2 views of the same storage): an fr_t limb IS such a word,
+// so no 32-bit halves have to be packed or unpacked around a load or a store
 B381_DI fr_t tile_get(const ntt_tile& t, uint32_t pos) {
   pos = ntt_tile_slot(pos);
+#if defined(__CUDA_ARCH__)
+  const ulonglong2 a = reinterpret_cast<const ulonglong2*>(t.lo)[pos], b = reinterpret_cast<const ulonglong2*>(t.hi)[pos];
+  fr_t r;
+  r.l[0] = a.x; r.l[1] = a.y; r.l[2] = b.x; r.l[3] = b.y;
+  return r;
+#else
   uint4 a = t.lo[pos], b = t.hi[pos];
   fr_t r;
   r.l[0] = ((uint64_t)a.y << 32) | a.x; r.l[1] = ((uint64_t)a.w << 32) | a.z;
   r.l[2] = ((uint64_t)b.y << 32) | b.x; r.l[3] = ((uint64_t)b.w << 32) | b.z;
   return r;
+#endif
 }
 B381_DI void tile_put(const ntt_tile& t, uint32_t pos, const fr_t& v) {
+#if defined(__CUDA_ARCH__)
+  pos = ntt_tile_slot(pos);
+  reinterpret_cast<ulonglong2*>(t.lo)[pos] = make_ulonglong2(v.l[0], v.l[1]);
+  reinterpret_cast<ulonglong2*>(t.hi)[pos] = make_ulonglong2(v.l[2], v.l[3]);
+#else
   uint4 a, b;
   a.x = (uint32_t)v.l[0]; a.y = (uint32_t)(v.l[0] >> 32); a.z = (uint32_t)v.l[1]; a.w = (uint32_t)(v.l[1] >> 32);
   b.x = (uint32_t)v.l[2]; b.y = (uint32_t)(v.l[2] >> 32); b.z = (uint32_t)v.l[3]; b.w = (uint32_t)(v.l[3] >> 32);
   pos = ntt_tile_slot(pos);
   t.lo[pos] = a;
   t.hi[pos] = b;
+#endif
 }
 
 B381_DI fr_t fr_gload(const fr_t* p) {
 #if defined(__CUDA_ARCH__)
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = q[0], b = q[1];
+  const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
+  const ulonglong2 a = q[0], b = q[1];
   fr_t r;
-  r.l[0] = ((uint64_t)a.y << 32) | a.x; r.l[1] = ((uint64_t)a.w << 32) | a.z;
-  r.l[2] = ((uint64_t)b.y << 32) | b.x; r.l[3] = ((uint64_t)b.w << 32) | b.z;
+  r.l[0] = a.x; r.l[1] = a.y; r.l[2] = b.x; r.l[3] = b.y;
   return r;
 #else
   return *p;
@@ -114,11 +128,10 @@ B381_DI fr_t fr_gload(const fr_t* p) {
 }
 B381_DI fr_t fr_gload_ro(const fr_t* p) {   // read-only path (twiddles, scale tables)
 #if defined(__CUDA_ARCH__)
-  const uint4* q = reinterpret_cast<const uint4*>(p);
-  uint4 a = __ldg(q), b = __ldg(q + 1);
+  const ulonglong2* q = reinterpret_cast<const ulonglong2*>(p);
+  const ulonglong2 a = __ldg(q), b = __ldg(q + 1);
   fr_t r;
-  r.l[0] = ((uint64_t)a.y << 32) | a.x; r.l[1] = ((uint64_t)a.w << 32) | a.z;
-  r.l[2] = ((uint64_t)b.y << 32) | b.x; r.l[3] = ((uint64_t)b.w << 32) | b.z;
+  r.l[0] = a.x; r.l[1] = a.y; r.l[2] = b.x; r.l[3] = b.y;
   return r;
 #else
   return *p;
@@ -135,12 +148,9 @@ B381_DI void fr_gstore256(fr_t* p, const fr_t& v) {
 }
 B381_DI void fr_gstore(fr_t* p, const fr_t& v) {
 #if defined(__CUDA_ARCH__)
-  uint4* q = reinterpret_cast<uint4*>(p);
-  uint4 a, b;
-  a.x = (uint32_t)v.l[0]; a.y = (uint32_t)(v.l[0] >> 32); a.z = (uint32_t)v.l[1]; a.w = (uint32_t)(v.l[1] >> 32);
-  b.x = (uint32_t)v.l[2]; b.y = (uint32_t)(v.l[2] >> 32); b.z = (uint32_t)v.l[3]; b.w = (uint32_t)(v.l[3] >> 32);
-  q[0] = a;
-  q[1] = b;
+  ulonglong2* q = reinterpret_cast<ulonglong2*>(p);
+  q[0] = make_ulonglong2(v.l[0], v.l[1]);
+  q[1] = make_ulonglong2(v.l[2], v.l[3]);
 #else
   *p = v;
 #endif
