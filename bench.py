@@ -163,7 +163,7 @@ def run_reference(args):
         "ntt": {"metric": f"fr_ntt_elems_per_s", "value": r["ntt_elems_per_s"], "unit": "elements/s", "log_n": r["ntt_log_n"]},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------- GPU arm
@@ -421,8 +421,31 @@ def reference_gpu_leg(args, torch, np, L, lib, timed, sc, sc_host, bases, n, our
     return out
 
 
+_JSON_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE line, the JSON result: everything any library prints there (NCCL's version banner,
+    torch warnings) is sent to stderr by pointing fd 1 at fd 2; the result is written to the saved descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    data = (json.dumps(obj) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse()
+    _claim_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -796,7 +819,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(out), flush=True)
+        emit(out)
 
 
 if __name__ == "__main__":

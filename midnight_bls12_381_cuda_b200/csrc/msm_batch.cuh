@@ -154,21 +154,23 @@ B381_DI void msm_half_counts_body(uint32_t b, const uint32_t* offsets, uint32_t 
   counts[b] = (b < nbuckets && b % Bs != Bs - 1) ? (offsets[b + 1] - offsets[b] + 1) / 2 : 0u;
 }
 
-// Chunk-major level 0 (msm_core.cuh): run r = chunk * nbuckets + slot.  Its sums are WRITTEN bucket-major, i.e. in the
-// order (slot, chunk): position perm(r) = slot * nchunks + chunk of the second count array, whose exclusive scan
-// gives every run's first output position -- and, at chunk 0, the level-1 offsets of the bucket slots.
-B381_HD uint32_t msm_run_perm(uint32_t r, uint32_t nbuckets, uint32_t nchunks) {
-  const uint32_t chunk = r / nbuckets, slot = r - chunk * nbuckets;
-  return slot * nchunks + chunk;
+// Chunk-major level 0 (msm_core.cuh): run r = (b * nchunks + chunk) * S + slot (S slots and nchunks chunks per MSM).
+// Its sums are WRITTEN bucket-major, i.e. in the order (b, slot, chunk): position perm(r) = (b * S + slot) * nchunks +
+// chunk of the second count array, whose exclusive scan gives every run's first output position -- and, at chunk 0,
+// the level-1 offsets of the bucket slots.
+B381_HD uint32_t msm_run_perm(uint32_t r, uint32_t set_slots, uint32_t nchunks) {
+  const uint32_t g = r / set_slots, slot = r - g * set_slots;
+  const uint32_t b = g / nchunks, chunk = g - b * nchunks;
+  return (b * set_slots + slot) * nchunks + chunk;
 }
-B381_DI void msm_half_counts_runs_body(uint32_t r, const uint32_t* run_off, uint32_t nbuckets, uint32_t nchunks, uint32_t Bs,
-                                       uint32_t* counts, uint32_t* counts_bucket_major) {
+B381_DI void msm_half_counts_runs_body(uint32_t r, const uint32_t* run_off, uint32_t nbuckets, uint32_t set_slots,
+                                       uint32_t nchunks, uint32_t Bs, uint32_t* counts, uint32_t* counts_bucket_major) {
   const uint32_t nruns = nbuckets * nchunks;
   if (r > nruns) return;
   if (r == nruns) { counts[r] = 0; counts_bucket_major[r] = 0; return; }
-  const uint32_t h = (r % Bs != Bs - 1) ? (run_off[r + 1] - run_off[r] + 1) / 2 : 0u;   // nbuckets is a multiple of Bs
+  const uint32_t h = (r % Bs != Bs - 1) ? (run_off[r + 1] - run_off[r] + 1) / 2 : 0u;   // set_slots is a multiple of Bs
   counts[r] = h;
-  counts_bucket_major[msm_run_perm(r, nbuckets, nchunks)] = h;
+  counts_bucket_major[msm_run_perm(r, set_slots, nchunks)] = h;
 }
 
 // slot -> input pair.  src[k*stride] = position of the pair's first point (| PAIR_SINGLE when the bucket's
@@ -178,7 +180,7 @@ B381_DI void msm_half_counts_runs_body(uint32_t r, const uint32_t* run_off, uint
 template <int B>
 B381_DI void pair_walk(uint32_t slot0, uint32_t n_out, const uint32_t* in_off, const uint32_t* out_off,
                        uint32_t nbuckets, uint32_t* src, size_t stride, const uint32_t* dst_base = nullptr,
-                       uint32_t dst_nbuckets = 0, uint32_t dst_nchunks = 0, uint32_t* dst = nullptr) {
+                       uint32_t dst_set_slots = 0, uint32_t dst_nchunks = 0, uint32_t* dst = nullptr) {
   uint32_t b = 0, ob = 0, oe = 0, ib = 0, ie = 0, db = 0;
   if (slot0 < n_out) {
     // last bucket whose first output slot is <= slot0 (empty buckets share a start with their
@@ -191,7 +193,7 @@ B381_DI void pair_walk(uint32_t slot0, uint32_t n_out, const uint32_t* in_off, c
     b = lo;
     ob = out_off[b]; oe = out_off[b + 1];
     ib = in_off[b]; ie = in_off[b + 1];
-    if (dst_base) db = dst_base[msm_run_perm(b, dst_nbuckets, dst_nchunks)];
+    if (dst_base) db = dst_base[msm_run_perm(b, dst_set_slots, dst_nchunks)];
   }
 #ifndef B381_HOST_TEST
 #pragma unroll 1
@@ -203,7 +205,7 @@ B381_DI void pair_walk(uint32_t slot0, uint32_t n_out, const uint32_t* in_off, c
       if (j >= oe) {
         do { b++; ob = oe; oe = out_off[b + 1]; } while (j >= oe);
         ib = in_off[b]; ie = in_off[b + 1];
-        if (dst_base) db = dst_base[msm_run_perm(b, dst_nbuckets, dst_nchunks)];
+        if (dst_base) db = dst_base[msm_run_perm(b, dst_set_slots, dst_nchunks)];
       }
       s = ib + 2u * (j - ob);
       if (s + 1 >= ie) s |= PAIR_SINGLE;

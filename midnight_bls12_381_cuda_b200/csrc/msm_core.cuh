@@ -39,24 +39,30 @@ struct msm_shape {
   uint32_t f;        // precompute_factor (>= 1): point i has f stored multiples, at bases[i*f + k]
   uint32_t batch;    // MSMs folded into this pipeline run: MSM b owns bucket sets [b*Wf, (b+1)*Wf)
   uint32_t shared;   // 1: every MSM of the batch reads bases[0 .. n*f); 0: MSM b reads bases[b*n*f ..)
-  uint32_t chunk_log, nchunks;   // grouping granularity: scalar t belongs to chunk t >> chunk_log (see below)
+  uint32_t chunk_log, nchunks;   // grouping granularity: scalar i of an MSM belongs to its chunk i >> chunk_log; chunks PER MSM
 };
 
 // CHUNK-MAJOR GROUPING.  The level-0 gathers of the affine pre-reduction touch the bases at random: 2^28 gathers over
 // 1.6 GB at 2^24 points, DRAM-bound at 128 bytes per 48-byte x-coordinate.  So the entries are grouped by
-// (chunk of 2^chunk_log consecutive scalars, bucket slot) instead of by bucket slot alone: "run" r = chunk * nbuckets
-// + slot.  Level 0 pairs entries inside a run and visits the runs chunk by chunk, so at any moment the whole GPU
-// gathers from ONE 50 MB range of the bases, which the 126 MB L2 holds; it writes its sums bucket-major (a run's
-// sums land behind those of the same bucket's earlier chunks), so from level 1 on nothing knows about chunks.
+// (MSM of the batch, chunk of 2^chunk_log consecutive scalars of that MSM, bucket slot of that MSM) instead of by
+// bucket slot alone: "run" r = (b * nchunks + chunk) * S + slot, S = Wf * Bs slots per MSM, nchunks chunks per MSM.
+// Level 0 pairs entries inside a run and visits the runs chunk by chunk, so at any moment the whole GPU gathers from
+// ONE 100 MB range of the bases, which the 126 MB L2 holds; it writes its sums bucket-major (a run's sums land behind
+// those of the same bucket's earlier chunks), so from level 1 on nothing knows about chunks.
 // A chunk's entries occupy a fixed region of the sorted array (2^chunk_log * W entries), so a chunk can be
 // histogrammed, scanned and scattered on its own -- while later chunks of host-resident scalars are still crossing
 // PCIe (msm_sort.cu).  nchunks == 1 is the plain bucket-major grouping.
 B381_HD uint32_t msm_runs(const msm_shape& sh) { return sh.nchunks * sh.nbuckets; }
+B381_HD uint32_t msm_set_slots(const msm_shape& sh) { return sh.Wf * sh.Bs; }          // S: bucket slots of ONE MSM
 B381_HD void msm_shape_set_chunks(msm_shape& sh, uint32_t chunk_log) {
-  const uint64_t nt = (uint64_t)sh.n * sh.batch;
   sh.chunk_log = chunk_log;
-  sh.nchunks = chunk_log >= 32 ? 1u : (uint32_t)((nt + (1ull << chunk_log) - 1) >> chunk_log);
+  sh.nchunks = chunk_log >= 32 ? 1u : (uint32_t)(((uint64_t)sh.n + (1ull << chunk_log) - 1) >> chunk_log);
   if (sh.nchunks <= 1) { sh.nchunks = 1; sh.chunk_log = 31; }
+}
+// run of scalar i of MSM b whose digit maps to bucket slot `key` (key = b * S + slot, msm_digit_at)
+B381_HD size_t msm_run_of(const msm_shape& sh, uint32_t b, uint32_t i, uint32_t key) {
+  const uint32_t S = sh.Wf * sh.Bs;
+  return ((size_t)b * sh.nchunks + (i >> sh.chunk_log)) * S + (key - b * S);
 }
 
 // With precompute_factor f the caller supplies f*n bases, point i's multiples 2^(k*Wf*c) * P_i (k < f) stored
@@ -150,7 +156,7 @@ B381_DI uint32_t msm_fetch_add(uint32_t* p, uint32_t v) {
 // (nbuckets = Wf * (2^(c-1) + 1) slots) and only the GROUPING matters, not the order inside a bucket -- the bucket
 // sum is the same group element whatever the order, and the MSM result is its unique affine form:
 //   pass 1 (this body)   hist[run]++ for every (scalar, window)            -- 2^28 REDs at 2^24 points, 1.2 ms on B200
-//                        (run = chunk * nbuckets + key: see CHUNK-MAJOR GROUPING above)
+//                        (run: see CHUNK-MAJOR GROUPING above; = key when there is one chunk)
 //   scan                 offsets = exclusive scan of hist (msm_sort.cu)    -- these ARE the bucket boundaries
 //   pass 2 (next body)   vals[cursor[key]++] = val                         -- digits recomputed, no key array exists
 // The reference writes 2 x 32-bit keys/values per pair and radix-sorts all 32 key bits with CUB
@@ -164,7 +170,7 @@ B381_DI void msm_hist_body(uint32_t t, const fr_t* scalars, bool scalars_mont, c
   uint32_t carry = 0, key, val;
   for (uint32_t w = 0; w < sh.W; w++) {
     msm_digit_at(s, sh, i, b, w, carry, key, val);
-    msm_fetch_add(hist + (size_t)(t >> sh.chunk_log) * sh.nbuckets + key, 1u);
+    msm_fetch_add(hist + msm_run_of(sh, b, i, key), 1u);
   }
 }
 
@@ -187,7 +193,7 @@ B381_DI void msm_scatter_body(uint32_t t, const fr_t* scalars, bool scalars_mont
 #pragma unroll
 #endif
     for (uint32_t j = 0; j < 8; j++)
-      if (w0 + j < sh.W) pos[j] = msm_fetch_add(cursor + (size_t)(t >> sh.chunk_log) * sh.nbuckets + key[j], 1u);
+      if (w0 + j < sh.W) pos[j] = msm_fetch_add(cursor + msm_run_of(sh, b, i, key[j]), 1u);
 #ifndef B381_HOST_TEST
 #pragma unroll
 #endif

@@ -44,9 +44,10 @@ static __global__ void k_msm_half_counts(const uint32_t* offsets, uint32_t nbuck
   msm_half_counts_body(b, offsets, nbuckets, Bs, counts);
 }
 
-static __global__ void k_msm_half_counts_runs(const uint32_t* run_off, uint32_t nbuckets, uint32_t nchunks, uint32_t Bs,
-                                              uint32_t* counts, uint32_t* counts_bucket_major) {
-  msm_half_counts_runs_body(blockIdx.x * blockDim.x + threadIdx.x, run_off, nbuckets, nchunks, Bs, counts, counts_bucket_major);
+static __global__ void k_msm_half_counts_runs(const uint32_t* run_off, uint32_t nbuckets, uint32_t set_slots, uint32_t nchunks,
+                                              uint32_t Bs, uint32_t* counts, uint32_t* counts_bucket_major) {
+  msm_half_counts_runs_body(blockIdx.x * blockDim.x + threadIdx.x, run_off, nbuckets, set_slots, nchunks, Bs, counts,
+                            counts_bucket_major);
 }
 // bucket slot k's level-1 entries start where its chunk-0 run's sums were written
 static __global__ void k_msm_level1_offsets(const uint32_t* dst_base, uint32_t nbuckets, uint32_t nchunks, uint32_t* off1) {
@@ -63,7 +64,7 @@ template <class F>
 void launch_pair_level(bool level0, const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets,
                        const uint32_t* svals, const level_pts<F> pts, size_t npts, unsigned grid, uint32_t* srcg, F* preg,
                        F* tot, F* outx, F* outy, cudaStream_t st, const uint32_t* dst_base = nullptr,
-                       uint32_t dst_nbuckets = 0, uint32_t dst_nchunks = 0, uint32_t* dst_slots = nullptr);
+                       uint32_t dst_set_slots = 0, uint32_t dst_nchunks = 0, uint32_t* dst_slots = nullptr);
 
 // window sums from the buckets, four lanes per segment: msm_tail.cu
 template <class F>
@@ -250,22 +251,21 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
     if (e && e[0]) levels = atoi(e);
     if (levels > 16) levels = 16;
   }
-  // chunk-major grouping (msm_core.cuh) when level 0 runs and the bases are several times larger than the L2 can hold:
-  // chunks of 100 MB of bases (2^20 G1 / 2^19 G2 points), from 8 chunks up, at most 64.  Measured on B200
+  // chunk-major grouping (msm_core.cuh) when level 0 runs and the bases of ONE MSM are several times larger than the L2
+  // can hold: chunks of 100 MB of bases (2^20 G1 / 2^19 G2 points), from 8 chunks up, at most 64.  Measured on B200
   // (profiles/r02d_msm_chunk_sweep.txt): 2^24 points 77.5 -> 74.3 ms (level-0 forward pass 10.7 -> 7.0 ms), 2^23
   // 40.7 -> 39.6; chunks of 2^19 / 2^18 are slower (shorter runs: more carried-over singles), 2^22 points gain nothing.
   {
     const bool g1 = sizeof(F) == sizeof(fq_t);
     uint32_t chunk_log = g1 ? 20u : 19u;
-    const uint64_t nt = (uint64_t)n * batch;
-    bool worth = levels >= 1 && nt >= (8ull << chunk_log);
+    bool worth = levels >= 1 && (uint64_t)n >= (8ull << chunk_log);
     if (const char* e = getenv("B381_MSM_CHUNK_LOG")) {          // A/B runs and tests: any size, 31 = off
       chunk_log = (uint32_t)atoi(e);
-      worth = levels >= 1 && chunk_log < 31 && nt > (1ull << chunk_log);
+      worth = levels >= 1 && chunk_log < 31 && (uint64_t)n > (1ull << chunk_log);
     }
-    while (chunk_log < 31 && ((nt + (1ull << chunk_log) - 1) >> chunk_log) > 64) chunk_log++;
+    while (chunk_log < 31 && (((uint64_t)n + (1ull << chunk_log) - 1) >> chunk_log) > 64) chunk_log++;
     if (worth) msm_shape_set_chunks(sh, chunk_log);
-    if ((uint64_t)msm_runs(sh) >= (1ull << 31)) msm_shape_set_chunks(sh, 31);
+    if ((uint64_t)sh.nchunks * sh.nbuckets >= (1ull << 31)) msm_shape_set_chunks(sh, 31);
   }
   const size_t nruns = msm_runs(sh);
 
@@ -325,7 +325,8 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
         uint32_t* half_bm;
         B381_CUDA_TRY(sc.alloc(&half_bm, nb_l + 1));
         B381_CUDA_TRY(sc.alloc(&dst_base, nb_l + 1));
-        k_msm_half_counts_runs<<<grid_for(nb_l + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, sh.nchunks, sh.Bs, half, half_bm);
+        k_msm_half_counts_runs<<<grid_for(nb_l + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, msm_set_slots(sh), sh.nchunks, sh.Bs,
+                                                                        half, half_bm);
         B381_CUDA_TRY(exclusive_scan_u32(sc, half_bm, dst_base, nb_l + 1, nullptr, &launches));
       } else {
         k_msm_half_counts<<<grid_for(nb_l + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, sh.Bs, half);
@@ -344,7 +345,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
         if (sh.nchunks > 1) B381_CUDA_TRY(sc.alloc(&dstg, nt_max * PB));
       }
       launch_pair_level<F>(l == 0, in_off, out_off, (uint32_t)nb_l, l == 0 ? svals : nullptr, acc_pts, npts, g, srcg, preg,
-                           tot, bufx[l & 1], bufy[l & 1], st, dst_base, sh.nbuckets, sh.nchunks, dstg);
+                           tot, bufx[l & 1], bufy[l & 1], st, dst_base, msm_set_slots(sh), sh.nchunks, dstg);
       acc_pts = level_from_xy<F>(bufx[l & 1], bufy[l & 1]);
       acc_vals = nullptr;
       if (chunked) {

@@ -10,7 +10,7 @@ namespace b381 {
 
 // thread t owns output slots [t*B, t*B + B); nt = threads in the grid = stride of the slot-major scratch
 // chunk-major level 0 (msm_core.cuh): "buckets" are runs and dst_base / dstg carry where each slot's sum is written
-struct pair_dst { const uint32_t* base; uint32_t nbuckets, nchunks; uint32_t* slots; };
+struct pair_dst { const uint32_t* base; uint32_t set_slots, nchunks; uint32_t* slots; };
 
 template <class F, int B, bool L0>
 __global__ void __launch_bounds__(PR_TPB, 4) k_msm_pair_fwd(const uint32_t* in_off, const uint32_t* out_off,
@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(PR_TPB, 4) k_msm_pair_fwd(const uint32_t* in_o
   const uint32_t n_out = out_off[nbuckets];
   const uint32_t t = blockIdx.x * PR_TPB + threadIdx.x;
   if ((uint64_t)t * B >= n_out) return;
-  pair_walk<B>(t * B, n_out, in_off, out_off, nbuckets, srcg + t, nt, dst.base, dst.nbuckets, dst.nchunks,
+  pair_walk<B>(t * B, n_out, in_off, out_off, nbuckets, srcg + t, nt, dst.base, dst.set_slots, dst.nchunks,
                dst.base ? dst.slots + t : nullptr);
   tot[t] = pair_phase1<F, B, L0>(srcg + t, nt, svals, pts, preg + t, nt, xs);
 }
@@ -115,9 +115,9 @@ int msm_pair_levels(double avg, size_t total) {
 template <class F>
 void launch_pair_level(bool level0, const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets,
                        const uint32_t* svals, const level_pts<F> pts, size_t npts, unsigned grid, uint32_t* srcg, F* preg,
-                       F* tot, F* outx, F* outy, cudaStream_t st, const uint32_t* dst_base, uint32_t dst_nbuckets,
+                       F* tot, F* outx, F* outy, cudaStream_t st, const uint32_t* dst_base, uint32_t dst_set_slots,
                        uint32_t dst_nchunks, uint32_t* dst_slots) {
-  const pair_dst dst{dst_base, dst_nbuckets, dst_nchunks, dst_slots};
+  const pair_dst dst{dst_base, dst_set_slots, dst_nchunks, dst_slots};
   if (level0) launch_level<F, true>(in_off, out_off, nbuckets, svals, pts, npts, grid, srcg, preg, tot, outx, outy, dst, st);
   else launch_level<F, false>(in_off, out_off, nbuckets, nullptr, pts, npts, grid, srcg, preg, tot, outx, outy, dst, st);
 }

@@ -148,7 +148,9 @@ cudaError_t msm_sort_pairs(Scratch& sc, const fr_t* d_scalars, bool scalars_mont
   if (e == cudaSuccess) e = cudaEventRecord(ready, st);             // d_scalars is a stream-ordered allocation of `st`
   if (e == cudaSuccess) e = cudaStreamWaitEvent(cp, ready, 0);
   if (e == cudaSuccess) cudaEventDestroy(ready);
-  const bool per_piece = sh.nchunks > 1;                            // chunks are self-contained: sort piece by piece
+  // chunks are self-contained: sort piece by piece (one MSM: in a batch the chunks of MSM b start at b * n, which
+  // the fixed-size pieces of the flattened scalar array do not respect)
+  const bool per_piece = sh.nchunks > 1 && sh.batch == 1;
   for (uint32_t first = 0; e == cudaSuccess && first < nt; first += piece) {
     const uint32_t end = nt - first < piece ? nt : first + piece;
     e = cudaMemcpyAsync(const_cast<fr_t*>(d_scalars) + first, host_src + first, sizeof(fr_t) * (end - first), cudaMemcpyHostToDevice, cp);

@@ -66,7 +66,7 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint
     if (chunked) {
       half_bm.assign(nb_l + 1, 0xdeadbeef);
       dst_base.assign(nb_l + 1, 0);
-      for (uint32_t r = 0; r <= nb_l; r++) msm_half_counts_runs_body(r, offsets.data(), sh.nbuckets, sh.nchunks, sh.Bs, half.data(), half_bm.data());
+      for (uint32_t r = 0; r <= nb_l; r++) msm_half_counts_runs_body(r, offsets.data(), sh.nbuckets, msm_set_slots(sh), sh.nchunks, sh.Bs, half.data(), half_bm.data());
       uint32_t acc2 = 0;
       for (uint32_t r = 0; r <= nb_l; r++) { dst_base[r] = acc2; acc2 += half_bm[r]; }
     } else {
@@ -81,7 +81,7 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint
     std::vector<uint32_t> srcg((size_t)NT * PB), dstg((size_t)NT * PB, 0xdeadbeef);
     std::vector<F> preg((size_t)NT * PB), tot(NT);
     for (uint32_t t = 0; t < NT; t++) {
-      if (chunked) pair_walk<PB>(t * PB, n_out, offsets.data(), next_off.data(), nb_l, srcg.data() + t, NT, dst_base.data(), sh.nbuckets, sh.nchunks, dstg.data() + t);
+      if (chunked) pair_walk<PB>(t * PB, n_out, offsets.data(), next_off.data(), nb_l, srcg.data() + t, NT, dst_base.data(), msm_set_slots(sh), sh.nchunks, dstg.data() + t);
       else pair_walk<PB>(t * PB, n_out, offsets.data(), next_off.data(), nb_l, srcg.data() + t, NT);
       tot[t] = l == 0 ? pair_phase1<F, PB, true>(srcg.data() + t, NT, cur_vals, cur, preg.data() + t, NT)
                       : pair_phase1<F, PB, false>(srcg.data() + t, NT, nullptr, cur, preg.data() + t, NT);
