@@ -3,7 +3,7 @@
 //
 // Algorithm (ours; the reference's is bls12-381/src/field/ntt_kernels.cu:110-958):
 //   * decimation-in-frequency radix-2 over log2(N) stages, grouped into PASSES of S stages; a pass keeps a
-//     2^TL-element tile in shared memory (TL = 11: 64 KB), so N = 2^24 is 3 trips through HBM (8 + 8 + 8 stages)
+//     2^TL-element tile in shared memory (TL = 10: 32 KB), so N = 2^24 is 3 trips through HBM (8 + 8 + 8 stages)
 //     instead of the reference's 12 radix-4 passes + bit-reversal pass + D2D copy (:772-810).
 //   * stage k butterfly on (i, i+2^k):  (a, b) -> (a+b, (a-b) * w),  w = omega_{2^(k+1)}^(i mod 2^k).
 //     Inside a pass two stages are run at a time on FOUR tile slots held in registers (a radix-4 step: 4 butterflies,
@@ -375,7 +375,12 @@ B381_DI void ntt_inverse_twiddle(uint64_t idx, const fr_t* fwd, fr_t* inv_table)
 }
 
 // ---- pass planner (host) --------------------------------------------------------------------
-constexpr uint32_t kNttTileLog = 11;   // 2048 elements = 64 KB of shared memory per CTA
+// 1024 elements = 32 KB of shared memory per CTA, 256 threads (one radix-4 group per thread and step), 3 CTAs per SM.
+// Measured on B200 against the 2048-element tile of round 1 (same threads and CTAs per SM, two groups per thread):
+// 2^24 3.55 -> 3.45 ms, 2^22 0.852 -> 0.826, 2^20 0.250 -> 0.222 (now three passes), 256 x 2^16 2.27 -> 2.21
+// (profiles/r02_ntt_variants.txt): the 96 KB of shared memory the smaller tiles leave go to the L1, which serves the
+// twiddle reads.  128 threads x 6 CTAs on the same tile: 3.74 ms.
+constexpr uint32_t kNttTileLog = 10;
 struct ntt_pass_plan { uint32_t lo, S, g, x; };
 
 // Splits the n stages into passes for a 2^tl-element tile.  The last pass (lo = 0) works on contiguous tiles and may
