@@ -20,6 +20,8 @@
 #define B381_HD __host__ __device__ __forceinline__
 #endif
 
+#include "inv_bingcd.cuh"
+
 namespace b381 {
 
 // ------------------------------------------------------------------ constants
@@ -137,6 +139,25 @@ B381_HD void raw6_shl1(uint64_t* a) {
   for (int i = 5; i > 0; i--) a[i] = (a[i] << 1) | (a[i - 1] >> 63);
   a[0] <<= 1;
 }
+// Variable-time inversion of a Montgomery-form element: the integer held in `a` is A = a*R; the binary GCD of
+// inv_bingcd.cuh gives A^-1 (mod p) and one Montgomery product with R^3 turns it into a^-1 * R.  inv(0) = 0.
+// (Round 1's Kaliski almost-inverse below is kept for A/B runs: -DB381_INV_KALISKI.)
+#ifndef B381_INV_KALISKI
+B381_DI fq_t inv_vartime(const fq_t& a) {
+  const uint64_t P[6] = FQ_MODULUS_INIT;
+  uint32_t y[12], m[12], o[12];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    y[2 * i] = (uint32_t)a.l[i]; y[2 * i + 1] = (uint32_t)(a.l[i] >> 32);
+    m[2 * i] = (uint32_t)P[i];   m[2 * i + 1] = (uint32_t)(P[i] >> 32);
+  }
+  bingcd_inverse<12>(y, m, FQ_INV32, kFqInvRounds, o);
+  fq_t x;
+#pragma unroll
+  for (int i = 0; i < 6; i++) x.l[i] = ((uint64_t)o[2 * i + 1] << 32) | o[2 * i];
+  return mul(x, fq_t{FQ_R3_INIT});
+}
+#else
 B381_DI fq_t inv_vartime(const fq_t& a) {
   if (is_zero(a)) return a;
   const uint64_t P[6] = FQ_MODULUS_INIT;
@@ -190,6 +211,7 @@ B381_DI fq_t inv_vartime(const fq_t& a) {
   x = mul(x, c2);
   return mul(x, c3);
 }
+#endif
 
 // r = a^e for a 64-bit exponent (twiddle / coset power setup)
 template <class F>

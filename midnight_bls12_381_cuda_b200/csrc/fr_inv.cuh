@@ -33,6 +33,23 @@ B381_HD uint64_t rawn_sub(uint64_t* r, const uint64_t* a, const uint64_t* b) {
   return br;
 }
 
+#ifndef B381_INV_KALISKI
+// binary GCD on the integer A = a*R (inv_bingcd.cuh), then one Montgomery product with R^3: a^-1 * R; inv(0) = 0
+B381_DI fr_t inv_vartime(const fr_t& a) {
+  const uint64_t P[4] = FR_MODULUS_INIT;
+  uint32_t y[8], m[8], o[8];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    y[2 * i] = (uint32_t)a.l[i]; y[2 * i + 1] = (uint32_t)(a.l[i] >> 32);
+    m[2 * i] = (uint32_t)P[i];   m[2 * i + 1] = (uint32_t)(P[i] >> 32);
+  }
+  bingcd_inverse<8>(y, m, FR_INV32, kFrInvRounds, o);
+  fr_t x;
+#pragma unroll
+  for (int i = 0; i < 4; i++) x.l[i] = ((uint64_t)o[2 * i + 1] << 32) | o[2 * i];
+  return mul(x, fr_t{FR_R3_INIT});
+}
+#else
 B381_DI fr_t inv_vartime(const fr_t& a) {
   if (is_zero(a)) return a;
   constexpr int N = 4;
@@ -91,5 +108,6 @@ B381_DI fr_t inv_vartime(const fr_t& a) {
   x = mul(x, c2);
   return mul(x, c3);
 }
+#endif
 
 }  // namespace b381
