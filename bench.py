@@ -690,6 +690,9 @@ def main():
         g2_phases = []
         g2_ms, _, _ = timed(g2_step, args.steps, g2_phases)
         g2_ms /= args.steps
+        g2_info = (C.c_int * 4)()
+        lib.b381_msm_last_info(g2_info, 4)
+        g2_info = list(g2_info)
         g2 = {"metric": "g2_msm_2^20_points_per_s", "value": n2 / (g2_ms * 1e-3), "unit": "points/s", "ms_per_step": g2_ms,
               "phases_ms": [round(statistics.mean(c), 4) for c in zip(*g2_phases)][:8], "result": res2}
         del bases2
@@ -808,7 +811,21 @@ def main():
                                  "no library kernel is on the MSM path",
             "phases_ms": dict(zip(names, [round(x, 4) for x in ph[:8]])),
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks, "ntt": ntt, "vecops": vec_ops, "reference_gpu": ref_gpu,
-            "g2": None if g2 is None else {k: v for k, v in g2.items() if k != "result"},
+            "g2": None if g2 is None else dict(
+                {k: v for k, v in g2.items() if k != "result"},
+                msm_shape={"window_c": g2_info[0], "windows": g2_info[1], "affine_levels": g2_info[2]},
+                roofline=None if len(g2["phases_ms"]) < 5 else {
+                    "bound": "imad (integer pipe)", "kernel": "bucket accumulation: affine levels + k_msm_accumulate<fq2_t>",
+                    "algorithmic_unit": "9000 MAD per (point, window) insertion: one XYZZ mixed addition = 10 Fq2 products = 30 Fq "
+                                        "products (SURVEY.md 8d's G1 unit x 3); executed in the affine levels: 6 Fq2 products = 5400",
+                    "kernel_ms": g2["phases_ms"][3] + g2["phases_ms"][4],
+                    "achieved": (1 << 20) * g2_info[1] * 9000.0 / ((g2["phases_ms"][3] + g2["phases_ms"][4]) * 1e-3) / 1e9,
+                    "peak": imad_peak / 1e9, "unit": "GMAD/s",
+                    "frac": (1 << 20) * g2_info[1] * 9000.0 / ((g2["phases_ms"][3] + g2["phases_ms"][4]) * 1e-3) / imad_peak,
+                    "executed_frac": (1 << 20) * g2_info[1] * 5400.0 / ((g2["phases_ms"][3] + g2["phases_ms"][4]) * 1e-3) / imad_peak,
+                    "tail_ms": sum(g2["phases_ms"][5:8]),
+                    "note": "finalize + bucket reduction + window combine (tail_ms) are latency-bound chains of Fq2 products; "
+                            "ncu: profiles/r02e_g2_key_metrics.txt"}),
             "probes": {"imad_wide_mad_per_s": imad_peak, "fq_mul_per_s": fq_rate, "fr_mul_per_s": fr_rate},
             "result_check": check if world == 1 else shard_check,
             "ntt_fourstep": ntt_dist, "plonk_commit_round": commits,

@@ -9,4 +9,4 @@ from .msm import BatchMsmHandle, G2MsmHandle, GpuMsmContext, MsmError, MsmHandle
 from .ntt import GpuNttContext, NttError, NttHandle, get_root_of_unity  # noqa: F401
 from .stream import DeviceVec, GpuError, ManagedStream, ensure_backend_loaded, is_gpu_available, set_device  # noqa: F401
 from .types import TypeConverter  # noqa: F401
-from . import vecops  # noqa: F401
+from . import points, vecops  # noqa: F401

@@ -191,3 +191,25 @@ def test_subgroup_checks(cuda, b381):
         cfg = lib.b381_default_vecops_config()
         assert getattr(lib, name)(None, n, C.byref(cfg), b381.ptr(flags)) == 11
         assert getattr(lib, name)(b381.ptr(raw), -1, C.byref(cfg), b381.ptr(flags)) == 11
+
+
+def test_points_host_layer(cuda, b381):
+    """midnight_bls12_381_cuda_b200.points: the numpy-level wrappers over the same entry points"""
+    import midnight_bls12_381_cuda_b200 as M
+    import vectors_points as V
+    rng = P.SplitMix64(11)
+    pts = [P.g1_mul(rng.fr(), P.G1_GEN) for _ in range(9)] + [None]
+    aff = np.frombuffer(b"".join(P.g1_affine_mont_bytes(p) for p in pts), dtype=np.uint64).reshape(-1, 12)
+    jac = M.points.g1_affine_to_projective(aff)
+    assert (M.points.g1_projective_to_affine(jac) == aff).all()
+    assert M.points.g1_is_on_curve(aff).all() and M.points.g1_is_in_subgroup(aff).all()
+    M.points.validate_g1_bases(aff)
+    cases = V.g1_membership_cases()
+    raw = np.frombuffer(b"".join(P.g1_affine_mont_bytes(p) for p, _ in cases), dtype=np.uint64).reshape(-1, 12)
+    assert list(M.points.g1_is_in_subgroup(raw)) == [m for _, m in cases]
+    with pytest.raises(M.points.PointError):
+        M.points.validate_g1_bases(raw)
+    ks = [rng.fr() for _ in pts]
+    sc = np.frombuffer(b"".join(P.fr_bytes(k) for k in ks), dtype=np.uint64).reshape(-1, 4)
+    exp = b"".join(g1_jac_bytes(P.g1_mul(k, p), 1) for k, p in zip(ks, pts))
+    assert M.points.g1_scalar_mul(aff, sc).tobytes() == exp == M.points.g1_scalar_mul(aff, sc, glv=False).tobytes()

@@ -316,3 +316,28 @@ def test_subgroup_check_bodies(glv_sim):
                 f.write(enc(pt))
         got = subprocess.run([exe, "sub", group, path], capture_output=True, text=True, check=True).stdout.split()
         assert [int(x) for x in got] == [int(m) for _, m in cases], group
+
+
+def test_binary_gcd_inversion(tmp_path):
+    """csrc/inv_bingcd.cuh (Pornin's binary GCD on 64-bit approximations, the inversion behind inv_vartime): y^-1 mod p
+    and mod r against Python's pow for edge values (0, 1, m-1, powers of two around the 30/32/64-bit boundaries of the
+    approximation, values of every bit length) and 2000 random ones per field; also with one round fewer than shipped,
+    which the round-count bound says must still be enough."""
+    import random
+    exe = str(tmp_path / "inv_host_sim")
+    subprocess.run(["g++", "-O2", "-std=c++17", f"-I{HOST}", f"-I{CSRC}", "-o", exe, os.path.join(HOST, "inv_host_sim.cpp")], check=True)
+    rnd = random.Random(20261019)
+    for name, mod, nbytes, shipped in (("fq", P.P_MOD, 48, 27), ("fr", P.R_MOD, 32, 18)):
+        vals = [0, 1, 2, 3, mod - 1, mod - 2, (mod + 1) // 2, (1 << 30) - 1, 1 << 30, (1 << 31) - 1, 1 << 32, (1 << 64) - 1,
+                1 << 64, (1 << 96) + 1, 1 << (mod.bit_length() - 1)]
+        vals += [rnd.randrange(1 << k) % mod for k in range(1, mod.bit_length() + 1)]
+        vals += [rnd.randrange(mod) for _ in range(2000)]
+        path = str(tmp_path / (name + ".bin"))
+        with open(path, "wb") as f:
+            for v in vals:
+                f.write(v.to_bytes(nbytes, "little"))
+        for rounds in (0, shipped - 1):
+            out = subprocess.run([exe, name, str(rounds), path], capture_output=True, text=True, check=True).stdout.split()
+            assert len(out) == len(vals)
+            for v, o in zip(vals, out):
+                assert int.from_bytes(bytes.fromhex(o), "little") == (pow(v, -1, mod) if v else 0), (name, rounds, hex(v))
