@@ -125,9 +125,25 @@ B381_DI void g1_mul_table(const affine_t<fq_t>& p, xyzz_t<fq_t>* T) {
   }
 }
 
-B381_DI xyzz_t<fq_t> g1_mul_glv(const affine_t<fq_t>& p, const fr_t& k) {
+// k mod r for any 256-bit k (at most two subtractions: 2^256 < 3r); the split below needs k < r
+B381_DI fr_t fr_canonical(fr_t k) {
+  const uint64_t R[4] = FR_MODULUS_INIT;
+  for (int it = 0; it < 2; it++) {
+    uint64_t d[4], borrow = 0;
+    for (int i = 0; i < 4; i++) {
+      unsigned __int128 t = (unsigned __int128)k.l[i] - R[i] - borrow;
+      d[i] = (uint64_t)t;
+      borrow = (uint64_t)(t >> 64) ? 1 : 0;
+    }
+    if (!borrow) for (int i = 0; i < 4; i++) k.l[i] = d[i];
+  }
+  return k;
+}
+
+B381_DI xyzz_t<fq_t> g1_mul_glv(const affine_t<fq_t>& p, const fr_t& k_in) {
   xyzz_t<fq_t> acc = xyzz_identity<fq_t>();
   if (is_inf(p)) return acc;
+  const fr_t k = fr_canonical(k_in);
   uint64_t k1[2], k2[2];
   glv_decompose(k, k1, k2);
   xyzz_t<fq_t> T[15];

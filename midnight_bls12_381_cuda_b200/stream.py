@@ -129,19 +129,27 @@ class PinnedArray:
     """uint64 result buffer in page-locked host memory.  An is_async call copies its result device -> host on the
     call's stream; into pageable memory that copy blocks the calling thread until the whole call has run, into pinned
     memory it does not -- which is what lets two handles overlap (core/msm.rs:715-798 keeps its results in DeviceVecs
-    for the same reason)."""
+    for the same reason).  Blocks are recycled through a free list: cudaHostAlloc / cudaFreeHost cost a device-wide
+    synchronisation each, which would serialise the very calls this exists for."""
+
+    _free: dict = {}          # words -> [pointer, ...]
 
     def __init__(self, shape):
         self.shape = tuple(np.atleast_1d(shape))
-        n = int(np.prod(self.shape))
-        p = C.c_void_p()
-        L.check(L.lib().b381_host_alloc_pinned(C.byref(p), max(8, 8 * n)), "host_alloc_pinned")
-        self._p = p.value
-        self.array = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_uint64)), shape=(n,)).reshape(self.shape)
+        n = max(1, int(np.prod(self.shape)))
+        self._words = n
+        cached = PinnedArray._free.get(n)
+        if cached:
+            self._p = cached.pop()
+        else:
+            p = C.c_void_p()
+            L.check(L.lib().b381_host_alloc_pinned(C.byref(p), 8 * n), "host_alloc_pinned")
+            self._p = p.value
+        self.array = np.ctypeslib.as_array(C.cast(C.c_void_p(self._p), C.POINTER(C.c_uint64)), shape=(n,)).reshape(self.shape)
         self.array[...] = 0
 
     def take(self) -> np.ndarray:
-        """pageable copy of the contents; releases the pinned block"""
+        """pageable copy of the contents; the pinned block goes back to the free list"""
         out = self.array.copy()
         self.free()
         return out
@@ -149,7 +157,7 @@ class PinnedArray:
     def free(self) -> None:
         if self._p:
             self.array = None
-            L.lib().b381_host_free_pinned(C.c_void_p(self._p))
+            PinnedArray._free.setdefault(self._words, []).append(self._p)
             self._p = 0
 
     def __del__(self):

@@ -123,7 +123,7 @@ def test_g1_scalar_mul_glv_and_plain(cuda, b381):
     pts = [base_pts[i % 16] for i in range(n)]
     pts[5] = None
     bases = np.frombuffer(b"".join(P.g1_affine_mont_bytes(p) for p in pts), dtype=np.uint64).copy()
-    sc = np.frombuffer(b"".join(P.fr_bytes(k % P.R_MOD) for k in ks), dtype=np.uint64).copy()
+    sc = np.frombuffer(b"".join(P.fr_bytes(k) for k in ks), dtype=np.uint64).copy()
     exp = b"".join(g1_jac_bytes(P.g1_mul(k, p), 1) for k, p in zip(ks, pts))
     lib = b381.lib()
     for name in ("bls12_381_g1_scalar_mul_glv", "bls12_381_g1_scalar_mul"):

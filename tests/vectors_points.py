@@ -31,4 +31,4 @@ def glv_scalars():
     L = P.GLV_LAMBDA
     rng = P.SplitMix64(383)
     return [0, 1, 2, 15, 16, L - 1, L, L + 1, 2 * L - 1, 2 * L, L * L - 1, L * L, L * (L + 1), P.R_MOD - 1, P.R_MOD - 2,
-            (1 << 128) - 1, 1 << 128, (1 << 254) + 12345] + [rng.fr() for _ in range(12)]
+            (1 << 128) - 1, 1 << 128, (1 << 254) + 12345, P.R_MOD, P.R_MOD + 5, (1 << 256) - 1] + [rng.fr() for _ in range(12)]
