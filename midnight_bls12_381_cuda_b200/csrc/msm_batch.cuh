@@ -164,13 +164,28 @@ B381_HD uint32_t msm_run_perm(uint32_t r, uint32_t set_slots, uint32_t nchunks) 
   return (b * set_slots + slot) * nchunks + chunk;
 }
 B381_DI void msm_half_counts_runs_body(uint32_t r, const uint32_t* run_off, uint32_t nbuckets, uint32_t set_slots,
-                                       uint32_t nchunks, uint32_t Bs, uint32_t* counts, uint32_t* counts_bucket_major) {
+                                       uint32_t nchunks, uint32_t Bs, uint32_t* counts, uint32_t* counts_bucket_major,
+                                       uint32_t r_end = 0xFFFFFFFFu) {
   const uint32_t nruns = nbuckets * nchunks;
-  if (r > nruns) return;
-  if (r == nruns) { counts[r] = 0; counts_bucket_major[r] = 0; return; }
+  if (r_end > nruns) r_end = nruns;
+  if (r > r_end) return;                        // r_end < nruns: one piece of runs at a time (streamed level 0)
+  if (r == r_end) {                             // sentinel: the scan leaves the slot total of [.., r_end) here
+    counts[r] = 0;
+    if (r == nruns) counts_bucket_major[r] = 0;
+    return;
+  }
   const uint32_t h = (r % Bs != Bs - 1) ? (run_off[r + 1] - run_off[r] + 1) / 2 : 0u;   // set_slots is a multiple of Bs
   counts[r] = h;
   counts_bucket_major[msm_run_perm(r, set_slots, nchunks)] = h;
+}
+
+// Streamed level 0 (msm_impl.cuh): the forward pass runs once per piece of runs.  Does thread t (slots [t*B, t*B + B))
+// run in the piece that brought the slot total from lo to hi?  It does when the piece completes its B slots; the last
+// piece also takes the thread with the ragged end.
+B381_HD bool pair_piece_owns(uint32_t t, uint32_t B, uint32_t lo, uint32_t hi, bool final) {
+  const uint64_t first = (uint64_t)t * B;
+  if (first + B <= lo) return false;            // done with an earlier piece
+  return final ? first < hi : first + B <= hi;
 }
 
 // slot -> input pair.  src[k*stride] = position of the pair's first point (| PAIR_SINGLE when the bucket's
@@ -211,7 +226,7 @@ B381_DI void pair_walk(uint32_t slot0, uint32_t n_out, const uint32_t* in_off, c
       if (s + 1 >= ie) s |= PAIR_SINGLE;
       if (dst_base) dst[(size_t)k * stride] = db + (j - ob);
     }
-    src[(size_t)k * stride] = s;
+    if (src) src[(size_t)k * stride] = s;        // nullptr: destinations only (k_msm_pair_dst)
   }
 }
 

@@ -44,10 +44,12 @@ static __global__ void k_msm_half_counts(const uint32_t* offsets, uint32_t nbuck
   msm_half_counts_body(b, offsets, nbuckets, Bs, counts);
 }
 
+// runs [r_begin, r_end] (r_end = sentinel); the whole level: r_begin = 0, r_end >= the number of runs
 static __global__ void k_msm_half_counts_runs(const uint32_t* run_off, uint32_t nbuckets, uint32_t set_slots, uint32_t nchunks,
-                                              uint32_t Bs, uint32_t* counts, uint32_t* counts_bucket_major) {
-  msm_half_counts_runs_body(blockIdx.x * blockDim.x + threadIdx.x, run_off, nbuckets, set_slots, nchunks, Bs, counts,
-                            counts_bucket_major);
+                                              uint32_t Bs, uint32_t* counts, uint32_t* counts_bucket_major,
+                                              uint32_t r_begin = 0u, uint32_t r_end = 0xFFFFFFFFu) {
+  msm_half_counts_runs_body(r_begin + blockIdx.x * blockDim.x + threadIdx.x, run_off, nbuckets, set_slots, nchunks, Bs,
+                            counts, counts_bucket_major, r_end);
 }
 // bucket slot k's level-1 entries start where its chunk-0 run's sums were written
 static __global__ void k_msm_level1_offsets(const uint32_t* dst_base, uint32_t nbuckets, uint32_t nchunks, uint32_t* off1) {
@@ -65,6 +67,18 @@ void launch_pair_level(bool level0, const uint32_t* in_off, const uint32_t* out_
                        const uint32_t* svals, const level_pts<F> pts, size_t npts, unsigned grid, uint32_t* srcg, F* preg,
                        F* tot, F* outx, F* outy, cudaStream_t st, const uint32_t* dst_base = nullptr,
                        uint32_t dst_set_slots = 0, uint32_t dst_nchunks = 0, uint32_t* dst_slots = nullptr);
+
+// Streamed chunk-major level 0 (plugin call with host scalars): forward pass of one piece of runs while the next piece
+// is still crossing PCIe, then destinations + inversion + backward pass once every piece is in (msm_pair.cu)
+template <class F>
+void launch_pair_fwd_piece(const uint32_t* in_off, const uint32_t* out_off, const uint32_t* svals, const level_pts<F> pts,
+                           unsigned grid, unsigned piece_grid, uint32_t t0, uint32_t nb_search, bool final,
+                           const uint32_t* lo_dev, const uint32_t* hi_dev, uint32_t* srcg, F* preg, F* tot, cudaStream_t st);
+template <class F>
+void launch_pair_finish_streamed(const uint32_t* in_off, const uint32_t* out_off, uint32_t nbuckets, const uint32_t* svals,
+                                 const level_pts<F> pts, unsigned grid, uint32_t* srcg, F* preg, F* tot, F* outx, F* outy,
+                                 cudaStream_t st, const uint32_t* dst_base, uint32_t dst_set_slots, uint32_t dst_nchunks,
+                                 uint32_t* dst_slots);
 
 // window sums from the buckets, four lanes per segment: msm_tail.cu
 template <class F>
@@ -269,6 +283,41 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   }
   const size_t nruns = msm_runs(sh);
 
+  // plan of the affine levels.  The slot-major scratch (stride nt = grid * PR_TPB) and the ping-pong point buffers are
+  // allocated once, for the LARGEST level.  That is level 0 while total > nbuckets + 2, but the bound
+  // (in + nbuckets) / 2 + 1 GROWS from level to level on a sparse input (forced B381_MSM_LEVELS with few points per
+  // bucket), so take the maximum over the plan.  (Level 0 of a chunk-major run rounds up once per RUN, not once per
+  // bucket slot.)
+  constexpr int PB = pair_batch<F>::B;
+  size_t nt_max = 0, nt_buf[2] = {0, 0};        // scratch stride; point buffers of the even / odd levels
+  {
+    size_t in = total;
+    for (int l = 0; l < levels; l++) {
+      const size_t out = (in + (l == 0 ? nruns : (size_t)sh.nbuckets)) / 2 + 1;
+      const size_t nt_l = (size_t)grid_for(out, (size_t)PR_TPB * PB) * PR_TPB;
+      if (nt_l > nt_max) nt_max = nt_l;
+      if (nt_l > nt_buf[l & 1]) nt_buf[l & 1] = nt_l;
+      in = out;
+    }
+  }
+  F* bufx[2] = {nullptr, nullptr};              // ping-pong level outputs, struct of arrays (msm_batch.cuh level_pts)
+  F* bufy[2] = {nullptr, nullptr};
+  uint32_t *srcg = nullptr, *dstg = nullptr;
+  F *preg = nullptr, *tot = nullptr;
+  auto alloc_level_scratch = [&](int l) -> cudaError_t {
+    if (!bufx[l & 1]) {
+      B381_CUDA_TRY(sc.alloc(&bufx[l & 1], nt_buf[l & 1] * PB));
+      B381_CUDA_TRY(sc.alloc(&bufy[l & 1], nt_buf[l & 1] * PB));
+    }
+    if (!srcg) {
+      B381_CUDA_TRY(sc.alloc(&srcg, nt_max * PB));
+      B381_CUDA_TRY(sc.alloc(&preg, nt_max * PB));
+      B381_CUDA_TRY(sc.alloc(&tot, nt_max));
+      if (sh.nchunks > 1) B381_CUDA_TRY(sc.alloc(&dstg, nt_max * PB));
+    }
+    return cudaSuccess;
+  };
+
   // -- 1 histogram of the runs, 2 scan = run boundaries, 3 scatter (msm_sort.cu; no library sort)
   int launches = 0;
   uint32_t *vals, *hist, *run_off, *offsets, *counts, *task_start;
@@ -279,73 +328,97 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   B381_CUDA_TRY(sc.alloc(&task_start, (size_t)sh.nbuckets + 1));
   if (sh.nchunks > 1) B381_CUDA_TRY(sc.alloc(&offsets, (size_t)sh.nbuckets + 1));
   else offsets = run_off;                       // one chunk: runs ARE bucket slots
+
+  // Streamed level 0 (host scalars, chunk-major, one MSM, several pieces): a piece's runs are final as soon as the
+  // piece is scattered, so its share of the level-0 FORWARD pass (slot walk, x-gathers, prefix products) runs while the
+  // next piece is still crossing PCIe.  Slot numbers continue from piece to piece through a device word per piece
+  // (carry[p] = slots before piece p); a thread runs in the piece that completes its PB slots.  What needs every piece
+  // -- the bucket-major destinations, the batched inversion, the backward pass -- follows the last one.
+  static const bool stream_l0_off = [] { const char* e = getenv("B381_MSM_STREAM_L0"); return e && e[0] == '0'; }();
+  const bool streamed = levels >= 1 && sh.nchunks > 1 && !stream_l0_off && msm_sort_is_streamed(sh, host_scalars);
+  uint32_t *half0 = nullptr, *out_off0 = nullptr, *half_bm0 = nullptr, *dst_base0 = nullptr, *carry = nullptr;
+  const unsigned g0 = grid_for((total + nruns) / 2 + 1, (size_t)PR_TPB * PB);
+  const level_pts<F> base_pts = level_from_bases(d_bases);
+  uint32_t piece_no = 0;
+  msm_piece_fn after_piece = [&](size_t r0, size_t r1, bool last) -> cudaError_t {
+    const size_t cnt = r1 - r0 + 1;             // + the sentinel: the scan leaves the slot total up to r1 at out_off0[r1]
+    k_msm_half_counts_runs<<<grid_for(cnt, 256), 256, 0, st>>>(run_off, sh.nbuckets, msm_set_slots(sh), sh.nchunks, sh.Bs,
+                                                               half0, half_bm0, (uint32_t)r0, (uint32_t)r1);
+    B381_CUDA_TRY(exclusive_scan_u32(sc, half0 + r0, out_off0 + r0, cnt, nullptr, &launches, 0u, carry + piece_no,
+                                     carry + piece_no + 1));
+    // the host knows only an upper bound of the slots so far: one per two entries + one per run
+    uint64_t pts_end = (uint64_t)(r1 / sh.nbuckets) << sh.chunk_log;
+    if (pts_end > n) pts_end = n;
+    unsigned pg = grid_for((size_t)((pts_end * sh.W + r1) / 2 + 1), (size_t)PR_TPB * PB);
+    if (pg > g0 || last) pg = g0;
+    launch_pair_fwd_piece<F>(run_off, out_off0, vals, base_pts, g0, pg, 0u, (uint32_t)r1, last, carry + piece_no,
+                             carry + piece_no + 1, srcg, preg, tot, st);
+    launches += 2;
+    piece_no++;
+    return cudaGetLastError();
+  };
+  if (streamed) {
+    const size_t npieces = ((size_t)n + msm_sort_piece(sh) - 1) / msm_sort_piece(sh);
+    B381_CUDA_TRY(sc.alloc(&half0, nruns + 1));
+    B381_CUDA_TRY(sc.alloc(&out_off0, nruns + 1));
+    B381_CUDA_TRY(sc.alloc(&half_bm0, nruns + 1));
+    B381_CUDA_TRY(sc.alloc(&dst_base0, nruns + 1));
+    B381_CUDA_TRY(sc.alloc(&carry, npieces + 1));
+    B381_CUDA_TRY(alloc_level_scratch(0));
+    B381_CUDA_TRY(cudaMemsetAsync(carry, 0, sizeof(uint32_t), st));
+  }
   tm.mark("msm:sort");
-  B381_CUDA_TRY(msm_sort_pairs(sc, d_scalars, scalars_mont, sh, host_scalars, hist, run_off, vals, &launches));
+  B381_CUDA_TRY(msm_sort_pairs(sc, d_scalars, scalars_mont, sh, host_scalars, hist, run_off, vals, &launches,
+                               streamed ? &after_piece : nullptr));
   const uint32_t* svals = vals;
   tm.mark(nullptr);
   tm.mark(nullptr);     // (two phase slots kept: histogram / scatter / offsets were separately timed passes before)
   tm.mark("msm:affine_levels");
 
   // -- 3b affine pre-reduction levels (msm_batch.cuh): each halves every bucket
-  level_pts<F> acc_pts = level_from_bases(d_bases);
+  level_pts<F> acc_pts = base_pts;
   const uint32_t* acc_vals = svals;
   int n_levels = 0;
   {
     size_t max_in = total;
     const uint32_t* in_off = run_off;
-    F* bufx[2] = {nullptr, nullptr};              // ping-pong level outputs, struct of arrays (msm_batch.cuh level_pts)
-    F* bufy[2] = {nullptr, nullptr};
-    constexpr int PB = pair_batch<F>::B;
-    uint32_t *srcg = nullptr, *dstg = nullptr;
-    F *preg = nullptr, *tot = nullptr;
-    // The slot-major scratch (stride nt = grid * PR_TPB) and the ping-pong point buffers are allocated once, for the
-    // LARGEST level.  That is level 0 while total > nbuckets + 2, but the bound (in + nbuckets) / 2 + 1 GROWS from level
-    // to level on a sparse input (forced B381_MSM_LEVELS with few points per bucket), so take the maximum over the plan.
-    // (Level 0 of a chunk-major run rounds up once per RUN, not once per bucket slot.)
-    size_t nt_max = 0, nt_buf[2] = {0, 0};        // scratch stride; point buffers of the even / odd levels
-    {
-      size_t in = total;
-      for (int l = 0; l < levels; l++) {
-        const size_t out = (in + (l == 0 ? nruns : (size_t)sh.nbuckets)) / 2 + 1;
-        const size_t nt_l = (size_t)grid_for(out, (size_t)PR_TPB * PB) * PR_TPB;
-        if (nt_l > nt_max) nt_max = nt_l;
-        if (nt_l > nt_buf[l & 1]) nt_buf[l & 1] = nt_l;
-        in = out;
-      }
-    }
     for (int l = 0; l < levels; l++) {
       const bool chunked = l == 0 && sh.nchunks > 1;
       const size_t nb_l = chunked ? nruns : (size_t)sh.nbuckets;        // "buckets" of this level
       const size_t max_out = (max_in + nb_l) / 2 + 1;
-      uint32_t *half, *out_off, *dst_base = nullptr;
-      B381_CUDA_TRY(sc.alloc(&half, nb_l + 1));
-      B381_CUDA_TRY(sc.alloc(&out_off, nb_l + 1));
-      if (chunked) {
-        // sums are produced run by run (chunk-major) and WRITTEN bucket-major: second count array in (slot, chunk) order
-        uint32_t* half_bm;
-        B381_CUDA_TRY(sc.alloc(&half_bm, nb_l + 1));
-        B381_CUDA_TRY(sc.alloc(&dst_base, nb_l + 1));
-        k_msm_half_counts_runs<<<grid_for(nb_l + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, msm_set_slots(sh), sh.nchunks, sh.Bs,
-                                                                        half, half_bm);
-        B381_CUDA_TRY(exclusive_scan_u32(sc, half_bm, dst_base, nb_l + 1, nullptr, &launches));
-      } else {
-        k_msm_half_counts<<<grid_for(nb_l + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, sh.Bs, half);
-      }
-      B381_CUDA_TRY(exclusive_scan_u32(sc, half, out_off, nb_l + 1, nullptr, &launches));
-      launches += 4;      // half counts + forward, invert, backward
       const unsigned g = grid_for(max_out, (size_t)PR_TPB * PB);
-      if (!bufx[l & 1]) {
-        B381_CUDA_TRY(sc.alloc(&bufx[l & 1], nt_buf[l & 1] * PB));
-        B381_CUDA_TRY(sc.alloc(&bufy[l & 1], nt_buf[l & 1] * PB));
+      B381_CUDA_TRY(alloc_level_scratch(l));
+      uint32_t* dst_base = nullptr;
+      const uint32_t* out_off_l;
+      if (chunked && streamed) {
+        // forward pass done piece by piece under the copy (after_piece above)
+        dst_base = dst_base0;
+        out_off_l = out_off0;
+        B381_CUDA_TRY(exclusive_scan_u32(sc, half_bm0, dst_base0, nb_l + 1, nullptr, &launches));
+        launch_pair_finish_streamed<F>(in_off, out_off0, (uint32_t)nb_l, svals, acc_pts, g, srcg, preg, tot, bufx[0], bufy[0],
+                                       st, dst_base0, msm_set_slots(sh), sh.nchunks, dstg);
+        launches += 3;    // destinations, invert, backward
+      } else {
+        uint32_t *half, *out_off;
+        B381_CUDA_TRY(sc.alloc(&half, nb_l + 1));
+        B381_CUDA_TRY(sc.alloc(&out_off, nb_l + 1));
+        if (chunked) {
+          // sums are produced run by run (chunk-major) and WRITTEN bucket-major: second count array in (slot, chunk) order
+          uint32_t* half_bm;
+          B381_CUDA_TRY(sc.alloc(&half_bm, nb_l + 1));
+          B381_CUDA_TRY(sc.alloc(&dst_base, nb_l + 1));
+          k_msm_half_counts_runs<<<grid_for(nb_l + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, msm_set_slots(sh), sh.nchunks,
+                                                                          sh.Bs, half, half_bm);
+          B381_CUDA_TRY(exclusive_scan_u32(sc, half_bm, dst_base, nb_l + 1, nullptr, &launches));
+        } else {
+          k_msm_half_counts<<<grid_for(nb_l + 1, 256), 256, 0, st>>>(in_off, sh.nbuckets, sh.Bs, half);
+        }
+        B381_CUDA_TRY(exclusive_scan_u32(sc, half, out_off, nb_l + 1, nullptr, &launches));
+        launches += 4;      // half counts + forward, invert, backward
+        out_off_l = out_off;
+        launch_pair_level<F>(l == 0, in_off, out_off, (uint32_t)nb_l, l == 0 ? svals : nullptr, acc_pts, npts, g, srcg, preg,
+                             tot, bufx[l & 1], bufy[l & 1], st, dst_base, msm_set_slots(sh), sh.nchunks, dstg);
       }
-      if (!srcg) {
-        B381_CUDA_TRY(sc.alloc(&srcg, nt_max * PB));
-        B381_CUDA_TRY(sc.alloc(&preg, nt_max * PB));
-        B381_CUDA_TRY(sc.alloc(&tot, nt_max));
-        if (sh.nchunks > 1) B381_CUDA_TRY(sc.alloc(&dstg, nt_max * PB));
-      }
-      launch_pair_level<F>(l == 0, in_off, out_off, (uint32_t)nb_l, l == 0 ? svals : nullptr, acc_pts, npts, g, srcg, preg,
-                           tot, bufx[l & 1], bufy[l & 1], st, dst_base, msm_set_slots(sh), sh.nchunks, dstg);
       acc_pts = level_from_xy<F>(bufx[l & 1], bufy[l & 1]);
       acc_vals = nullptr;
       if (chunked) {
@@ -356,7 +429,7 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
         launches++;
         in_off = off1;
       } else {
-        in_off = out_off;
+        in_off = out_off_l;
       }
       max_in = max_out;
       avg *= 0.5;

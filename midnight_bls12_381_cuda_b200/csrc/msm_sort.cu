@@ -17,9 +17,12 @@ namespace b381 {
 // short launches beat a decoupled look-back single pass on latency.
 constexpr int SCAN_TPB = 256, SCAN_IPT = 16, SCAN_TILE = SCAN_TPB * SCAN_IPT;
 
+// base_dev / total_dev (single-tile launches only): a base value read from device memory and added to every prefix,
+// and where base + total goes -- a chain of scans over consecutive pieces of one array needs no host round trip
 static __global__ void __launch_bounds__(SCAN_TPB) k_scan_tile(const uint32_t* in, uint32_t* out, size_t n, uint32_t* tile_sums,
-                                                               uint32_t add) {
+                                                               uint32_t add, const uint32_t* base_dev, uint32_t* total_dev) {
   __shared__ uint32_t warp_tot[SCAN_TPB / 32];
+  if (base_dev) add += *base_dev;                  // read before anything is written: base_dev may alias out[0]
   const size_t base = (size_t)blockIdx.x * SCAN_TILE + (size_t)threadIdx.x * SCAN_IPT;
   uint32_t v[SCAN_IPT];
   const bool wide = base + SCAN_IPT <= n && ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
@@ -63,6 +66,7 @@ static __global__ void __launch_bounds__(SCAN_TPB) k_scan_tile(const uint32_t* i
       if (base + j < n) out[base + j] = v[j] + pre;
   }
   if (tile_sums && threadIdx.x == 0) tile_sums[blockIdx.x] = tile_total;
+  if (total_dev && threadIdx.x == 0) *total_dev = add + tile_total;
 }
 
 static __global__ void __launch_bounds__(256) k_scan_add(uint32_t* out, size_t n, const uint32_t* tile_offs, uint32_t* copy,
@@ -80,12 +84,12 @@ static __global__ void __launch_bounds__(256) k_copy_u32(const uint32_t* in, uin
 }
 
 cudaError_t exclusive_scan_u32(Scratch& sc, const uint32_t* in, uint32_t* out, size_t n, uint32_t* copy, int* launches,
-                               uint32_t base) {
+                               uint32_t base, const uint32_t* base_dev, uint32_t* total_dev) {
   if (n == 0) return cudaSuccess;
   cudaStream_t st = sc.stream();
   const size_t tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
   if (tiles == 1) {
-    k_scan_tile<<<1, SCAN_TPB, 0, st>>>(in, out, n, nullptr, base);
+    k_scan_tile<<<1, SCAN_TPB, 0, st>>>(in, out, n, nullptr, base, base_dev, total_dev);
     if (launches) (*launches)++;
     if (copy) {
       k_copy_u32<<<grid_for(n, 256), 256, 0, st>>>(out, copy, n);
@@ -95,9 +99,10 @@ cudaError_t exclusive_scan_u32(Scratch& sc, const uint32_t* in, uint32_t* out, s
   }
   uint32_t* sums;
   B381_CUDA_TRY(sc.alloc(&sums, tiles));
-  k_scan_tile<<<(unsigned)tiles, SCAN_TPB, 0, st>>>(in, out, n, sums, 0u);
+  k_scan_tile<<<(unsigned)tiles, SCAN_TPB, 0, st>>>(in, out, n, sums, 0u, nullptr, nullptr);
   if (launches) (*launches)++;
-  B381_CUDA_TRY(exclusive_scan_u32(sc, sums, sums, tiles, nullptr, launches, 0u));
+  // the device-side base and total travel with the scan of the tile totals: sums[i] = *base_dev + tiles before i
+  B381_CUDA_TRY(exclusive_scan_u32(sc, sums, sums, tiles, nullptr, launches, 0u, base_dev, total_dev));
   k_scan_add<<<grid_for(n, 256), 256, 0, st>>>(out, n, sums, copy, base);
   if (launches) (*launches)++;
   return cudaGetLastError();
@@ -122,8 +127,21 @@ static __global__ void __launch_bounds__(256) k_msm_scatter(const fr_t* scalars,
 // a copy stream (2^24 scalars = 512 MiB = 9.4 ms at 57 GB/s) and every piece is histogrammed as it lands; when the
 // grouping is chunk-major a piece is a whole number of chunks, each chunk owns a fixed region of the sorted array,
 // and the piece is scanned and scattered right away too, so the entire sort rides under the transfer.
+bool msm_sort_is_streamed(const msm_shape& sh, const fr_t* host_src) {
+  return host_src != nullptr && sh.nchunks > 1 && sh.batch == 1 && sh.n > msm_sort_piece(sh);
+}
+uint32_t msm_sort_piece(const msm_shape& sh) {
+  uint32_t piece = 1u << 21;                            // 64 MiB of scalars per copy
+  if (const char* e = getenv("B381_MSM_PIECE_LOG")) {   // tests: multi-piece runs at small sizes
+    const int v = atoi(e);
+    if (v >= 8 && v <= 26) piece = 1u << v;
+  }
+  if (sh.nchunks > 1 && (1u << sh.chunk_log) > piece) piece = 1u << sh.chunk_log;   // a piece is a whole number of chunks
+  return piece;
+}
+
 cudaError_t msm_sort_pairs(Scratch& sc, const fr_t* d_scalars, bool scalars_mont, const msm_shape& sh, const fr_t* host_src,
-                           uint32_t* hist, uint32_t* run_off, uint32_t* vals, int* launches) {
+                           uint32_t* hist, uint32_t* run_off, uint32_t* vals, int* launches, const msm_piece_fn* after_piece) {
   cudaStream_t st = sc.stream();
   const uint32_t nt = sh.n * sh.batch;                  // scalars of the whole batch, [batch][n]
   const size_t nruns = msm_runs(sh);
@@ -131,8 +149,7 @@ cudaError_t msm_sort_pairs(Scratch& sc, const fr_t* d_scalars, bool scalars_mont
   B381_CUDA_TRY(sc.alloc(&cursor, nruns + 1));
   // one spare slot: the scan of nruns + 1 entries leaves the pair total in run_off[nruns]
   B381_CUDA_TRY(cudaMemsetAsync(hist, 0, sizeof(uint32_t) * (nruns + 1), st));
-  uint32_t piece = 1u << 21;                            // 64 MiB of scalars per copy
-  if (sh.nchunks > 1 && sh.chunk_log > 21) piece = 1u << sh.chunk_log;
+  const uint32_t piece = msm_sort_piece(sh);
   if (!host_src || nt <= piece) {
     if (host_src) B381_CUDA_TRY(cudaMemcpyAsync(const_cast<fr_t*>(d_scalars), host_src, sizeof(fr_t) * nt, cudaMemcpyHostToDevice, st));
     k_msm_hist<<<grid_for(nt, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, hist, 0u, nt);
@@ -164,10 +181,14 @@ cudaError_t msm_sort_pairs(Scratch& sc, const fr_t* d_scalars, bool scalars_mont
     if (per_piece) {
       const size_t r0 = (size_t)(first >> sh.chunk_log) * sh.nbuckets;
       const size_t r1 = end == nt ? nruns + 1 : (size_t)(end >> sh.chunk_log) * sh.nbuckets;   // last piece: + the total slot
-      e = exclusive_scan_u32(sc, hist + r0, run_off + r0, r1 - r0, cursor + r0, launches, first * sh.W);
+      // one entry past the piece as well: run_off[r1] = where the NEXT piece starts (its counters are still zero), which
+      // the slot walk of a streamed level 0 reads as the end of the piece's last run
+      e = exclusive_scan_u32(sc, hist + r0, run_off + r0, (end == nt ? r1 : r1 + 1) - r0, cursor + r0, launches, first * sh.W);
       if (e != cudaSuccess) break;
       k_msm_scatter<<<grid_for(end - first, 256), 256, 0, st>>>(d_scalars, scalars_mont, sh, cursor, vals, first, end);
       if (launches) (*launches)++;
+      // the piece's runs are final: the caller may start level 0 on them while the next piece is in flight
+      if (after_piece && (e = (*after_piece)(r0, end == nt ? nruns : r1, end == nt)) != cudaSuccess) break;
     }
   }
   cudaStreamDestroy(cp);                                            // deferred by the runtime until its copies are done

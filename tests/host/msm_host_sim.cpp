@@ -1,7 +1,7 @@
 // CPU-only driver for the per-thread MSM bodies in csrc/msm_core.cuh (TEST INFRASTRUCTURE).
 // Runs exactly the kernel pipeline of csrc/msm_impl.cuh with a serial loop per "kernel" and
 // a serial exclusive scan in place of the device scan.  Usage:
-//   msm_host_sim <g1|g2> <n> <c> <K> <L> <scalars_mont 0|1> <infile> [factor] [levels] [batch] [shared 0|1] [chunk_log]
+//   msm_host_sim <g1|g2> <n> <c> <K> <L> <scalars_mont 0|1> <infile> [factor] [levels] [batch] [shared 0|1] [chunk_log] [piece_chunks]
 // chunk_log < 31 (with levels >= 1) groups the entries chunk-major exactly as msm_impl.cuh does for large inputs.
 // prints one result per MSM of the batch (hex, std form).  batch > 1 folds the MSMs into one pipeline run exactly as
 // msm_impl.cuh does (scalars [batch][n]; points shared or [batch][n]).
@@ -21,7 +21,7 @@ using namespace b381;
 
 template <class F>
 int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint32_t factor, uint32_t levels,
-        uint32_t batch, bool shared, uint32_t chunk_log) {
+        uint32_t batch, bool shared, uint32_t chunk_log, uint32_t piece_chunks) {
   const uint32_t nsc = n * batch, np = shared ? n : n * batch;
   std::vector<fr_t> sc(nsc);
   std::vector<affine_t<F>> pts(np);
@@ -80,6 +80,38 @@ int run(uint32_t n, uint32_t c, uint32_t K, uint32_t L, bool mont, FILE* f, uint
     uint32_t NT = (n_out + PB - 1) / PB + 2;
     std::vector<uint32_t> srcg((size_t)NT * PB), dstg((size_t)NT * PB, 0xdeadbeef);
     std::vector<F> preg((size_t)NT * PB), tot(NT);
+    if (chunked && piece_chunks) {
+      // streamed level 0 as msm_impl.cuh runs it under the copy of host scalars: per piece of `piece_chunks` chunks the
+      // half counts of its runs (+ sentinel), a scan continued through a carried slot total, and the forward pass of the
+      // threads the piece completes -- each seeing only the offsets [0, r1] that exist by then; the bucket-major
+      // destinations follow in a second walk without loads
+      std::vector<uint32_t> h2(nb_l + 1, 0xdeadbeef), hb2(nb_l + 1, 0xdeadbeef), oo(nb_l + 1, 0xdeadbeef);
+      std::vector<int> ran(NT, 0);
+      uint32_t carry = 0;
+      for (uint32_t c0 = 0; c0 < sh.nchunks; c0 += piece_chunks) {
+        const uint32_t r0 = c0 * sh.nbuckets;
+        const bool last = c0 + piece_chunks >= sh.nchunks;
+        const uint32_t r1 = last ? nruns : (c0 + piece_chunks) * sh.nbuckets;
+        for (uint32_t r = r0; r <= r1; r++)
+          msm_half_counts_runs_body(r, offsets.data(), sh.nbuckets, msm_set_slots(sh), sh.nchunks, sh.Bs, h2.data(), hb2.data(), r1);
+        const uint32_t lo = carry;
+        for (uint32_t r = r0; r <= r1; r++) { oo[r] = carry; carry += h2[r]; }
+        const uint32_t hi = carry;
+        if (oo[r1] != hi) return 6;
+        for (uint32_t t = 0; t < NT; t++) {
+          if (!pair_piece_owns(t, PB, lo, hi, last)) continue;
+          if (ran[t]++) return 7;
+          pair_walk<PB>(t * PB, hi, offsets.data(), oo.data(), r1, srcg.data() + t, NT);
+          tot[t] = pair_phase1<F, PB, true>(srcg.data() + t, NT, cur_vals, cur, preg.data() + t, NT);
+        }
+      }
+      for (uint32_t r = 0; r <= nb_l; r++) if (oo[r] != next_off[r] || h2[r] != half[r] || hb2[r] != half_bm[r]) return 8;
+      for (uint32_t t = 0; t < NT; t++) {
+        if (((size_t)t * PB < n_out) != (ran[t] == 1)) return 9;
+        if ((size_t)t * PB < n_out)
+          pair_walk<PB>(t * PB, n_out, offsets.data(), next_off.data(), nb_l, nullptr, NT, dst_base.data(), msm_set_slots(sh), sh.nchunks, dstg.data() + t);
+      }
+    } else
     for (uint32_t t = 0; t < NT; t++) {
       if (chunked) pair_walk<PB>(t * PB, n_out, offsets.data(), next_off.data(), nb_l, srcg.data() + t, NT, dst_base.data(), msm_set_slots(sh), sh.nchunks, dstg.data() + t);
       else pair_walk<PB>(t * PB, n_out, offsets.data(), next_off.data(), nb_l, srcg.data() + t, NT);
@@ -144,8 +176,9 @@ int main(int argc, char** argv) {
   uint32_t batch = argc > 10 ? atoi(argv[10]) : 1;
   bool shared = argc > 11 ? atoi(argv[11]) != 0 : true;
   uint32_t chunk_log = argc > 12 ? atoi(argv[12]) : 31;
-  int rc = g2 ? run<fq2_t>(n, c, K, L, mont, f, factor, levels, batch, shared, chunk_log)
-              : run<fq_t>(n, c, K, L, mont, f, factor, levels, batch, shared, chunk_log);
+  uint32_t piece_chunks = argc > 13 ? atoi(argv[13]) : 0;    // > 0: level 0 streamed in pieces of that many chunks
+  int rc = g2 ? run<fq2_t>(n, c, K, L, mont, f, factor, levels, batch, shared, chunk_log, piece_chunks)
+              : run<fq_t>(n, c, K, L, mont, f, factor, levels, batch, shared, chunk_log, piece_chunks);
   fclose(f);
   return rc;
 }

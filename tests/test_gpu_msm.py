@@ -391,6 +391,29 @@ def test_chunk_major_grouping(cuda, b381, oracle, monkeypatch, chunk_log):
     assert raw_msm(b381, "g2", sc2, bases2, n2, c=8)[0].tobytes() == oracle.msm(2, sc2, bases2).tobytes()
 
 
+@pytest.mark.parametrize("chunk_log,piece_log", [("13", "14"), ("14", "14"), ("12", "15")])
+def test_streamed_level0(cuda, b381, oracle, monkeypatch, chunk_log, piece_log):
+    """Host scalars + chunk-major + several pieces: level 0's forward pass runs piece by piece while later pieces are
+    still being copied and sorted (msm_impl.cuh `streamed`), forced here at 2^16 points with 2^14 / 2^15-scalar pieces
+    of 1, 2 and 8 chunks.  Same bytes as the oracle; a zeroed piece (only trash slots), a ragged last chunk, G2."""
+    monkeypatch.setenv("B381_MSM_LEVELS", "2")
+    monkeypatch.setenv("B381_MSM_CHUNK_LOG", chunk_log)
+    monkeypatch.setenv("B381_MSM_PIECE_LOG", piece_log)
+    n = (1 << 16) + 777
+    bases = oracle.gen_series(1, [3, 0, 0, 0], [5, 0, 0, 0], n)
+    sc = oracle.random_fr(41, n)
+    sc[5], sc[6] = 0, sc[7]
+    assert raw_msm(b381, "g1", sc, bases, n, c=10)[0].tobytes() == oracle.msm(1, sc, bases).tobytes()
+    sc[1 << 14:1 << 15] = 0                                            # one piece with nothing but trash slots
+    assert raw_msm(b381, "g1", sc, bases, n, c=10)[0].tobytes() == oracle.msm(1, sc, bases).tobytes()
+    sc[:1 << 14] = 0                                                   # ... and the first piece as well
+    assert raw_msm(b381, "g1", sc, bases, n, c=9)[0].tobytes() == oracle.msm(1, sc, bases).tobytes()
+    n2 = 40000
+    bases2 = oracle.gen_series(2, [3, 0, 0, 0], [5, 0, 0, 0], n2)
+    sc2 = oracle.random_fr(43, n2)
+    assert raw_msm(b381, "g2", sc2, bases2, n2, c=8)[0].tobytes() == oracle.msm(2, sc2, bases2).tobytes()
+
+
 def test_chunk_major_host_scalars_large(cuda, b381, oracle, monkeypatch):
     """2^22 host scalars in two 2^21 pieces, chunk-major with 2^20 chunks: every piece is histogrammed, scanned and
     scattered while the next one is still in flight; checked against the discrete-log identity."""

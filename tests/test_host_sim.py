@@ -28,7 +28,8 @@ def sims(tmp_path_factory):
     return bins
 
 
-def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1, levels=0, batch=1, shared=True, chunk_log=31):
+def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1, levels=0, batch=1, shared=True, chunk_log=31,
+            piece_chunks=0):
     """batch > 1: `scalars` holds batch * n values ([batch][n]); returns the list of results"""
     path = os.path.join(sims["dir"], "msm_in.bin")
     with open(path, "wb") as f:
@@ -37,7 +38,8 @@ def run_msm(sims, group, scalars, pts, c, K, L, mont=True, factor=1, levels=0, b
         for pt in pts:
             f.write(P.g1_affine_mont_bytes(pt) if group == "g1" else P.g2_affine_mont_bytes(pt))
     r = subprocess.run([sims["msm_host_sim"], group, str(len(scalars) // batch), str(c), str(K), str(L), str(int(mont)), path,
-                        str(factor), str(levels), str(batch), str(int(shared)), str(chunk_log)],
+                        str(factor), str(levels), str(batch), str(int(shared)), str(chunk_log),
+                        str(piece_chunks)],
                        capture_output=True, text=True, check=True)
     out = [bytes.fromhex(x) for x in r.stdout.split()]
     return out[0] if batch == 1 else out
@@ -70,6 +72,37 @@ def test_msm_chunk_major_grouping(sims, tmp_path):
             dl = sum(s * k for s, k in zip(sc[b * n:(b + 1) * n], ks)) % P.R_MOD
             exp = P.g1_result_std_bytes(mul(dl, gen)) if group == "g1" else P.g2_result_std_bytes(mul(dl, gen))
             assert got[b] == exp, (group, n, batch, chunk_log, b)
+
+
+def test_msm_streamed_level0(sims, tmp_path):
+    """Level 0 of a chunk-major run streamed piece by piece (msm_impl.cuh, plugin call with host scalars): per piece the
+    half counts + a scan continued through the carried slot total, the forward pass of the threads that piece
+    completes (pair_piece_owns) seeing only the offsets that exist so far; destinations in a second walk.  The host
+    simulation checks that every thread runs exactly once and that the pieced scans equal the one-shot ones; the
+    result must equal the discrete-log ground truth.  Zero scalars (all-trash pieces), one- and many-chunk pieces,
+    a ragged last chunk; once under ASan + UBSan."""
+    exe = str(tmp_path / "msm_host_sim_asan")
+    subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-D_GLIBCXX_ASSERTIONS", f"-I{HOST}",
+                    f"-I{CSRC}", "-o", exe, os.path.join(HOST, "msm_host_sim.cpp")], check=True)
+    asan = dict(sims)
+    asan["msm_host_sim"] = exe
+    rng = P.SplitMix64(2024)
+    for (group, n, c, K, L, levels, chunk_log, piece_chunks, zeros, which) in [
+            ("g1", 70, 4, 3, 4, 3, 3, 1, (), sims), ("g1", 70, 4, 3, 4, 2, 3, 2, (), sims), ("g1", 100, 3, 4, 2, 4, 4, 3, (), asan),
+            ("g1", 64, 4, 3, 4, 2, 3, 2, range(16, 48), sims), ("g1", 40, 5, 3, 4, 1, 2, 3, range(0, 8), sims),
+            ("g2", 24, 4, 3, 4, 2, 2, 2, (), asan)]:
+        mul, gen = (P.g1_mul, P.G1_GEN) if group == "g1" else (P.g2_mul, P.G2_GEN)
+        ks = [rng.fr() for _ in range(n)]
+        pts = [mul(k, gen) for k in ks]
+        pts[7], ks[7] = pts[6], ks[6]
+        sc = [rng.fr() for _ in range(n)]
+        sc[7] = sc[6]
+        for i in zeros:
+            sc[i] = 0
+        got = run_msm(which, group, sc, pts, c, K, L, levels=levels, chunk_log=chunk_log, piece_chunks=piece_chunks)
+        dl = sum(s * k for s, k in zip(sc, ks)) % P.R_MOD
+        exp = P.g1_result_std_bytes(mul(dl, gen)) if group == "g1" else P.g2_result_std_bytes(mul(dl, gen))
+        assert got == exp, (group, n, chunk_log, piece_chunks)
 
 
 def test_msm_batch_folded_into_one_run(sims):
