@@ -497,9 +497,12 @@ def main():
     msm = D.ShardedMsm("g1")
     result = {}
 
+    part_buf = torch.empty(D.XYZZ_BYTES["g1"], dtype=torch.uint8, device="cuda")
+    gathered = torch.empty((world, D.XYZZ_BYTES["g1"]), dtype=torch.uint8, device="cuda")
+
     def step_resident():
-        part = msm.partial(sc, bases, n_loc, scalars_mont=True)
-        parts = D.gather_partials(part)
+        part = msm.partial(sc, bases, n_loc, scalars_mont=True, out=part_buf)
+        parts = D.gather_partials_into(part, gathered)
         if rank == 0:
             result["r"] = msm.combine(parts)
 
@@ -518,7 +521,7 @@ def main():
             result["e2e"] = e2e_res
         else:
             L.check(lib.b381_g1_msm_partial(L.ptr(sc_host), L.ptr(bases), n_loc, C.byref(host_cfg), L.ptr(e2e_part)), "plugin partial")
-            parts = D.gather_partials(e2e_part)
+            parts = D.gather_partials_into(e2e_part.view(torch.uint8), gathered)
             if rank == 0:
                 result["e2e"] = msm.combine(parts)               # D2H of the 144-byte result
 

@@ -273,6 +273,11 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
     const bool g1 = sizeof(F) == sizeof(fq_t);
     uint32_t chunk_log = g1 ? 20u : 19u;
     bool worth = levels >= 1 && (uint64_t)n >= (8ull << chunk_log);
+    // Host scalars (the plugin call): chunk-major also pays from FOUR chunks up for G1, because chunks are what lets the
+    // sort and level 0's forward pass run under the PCIe copy (msm_sort.cu pieces, `streamed` below).  Measured on B200
+    // (profiles/r02h_host_chunks.txt): 2^22 host scalars 23.96 -> 22.75 ms; 2^21 in four 2^19 chunks 13.78 -> 13.84 and
+    // G2 2^20 / 2^21 24.4 -> 25.1 / 40.5 -> 40.8 (no gain: not enabled); resident scalars gain nothing below 2^23.
+    if (!worth && g1 && host_scalars && batch == 1 && levels >= 1 && (uint64_t)n >= (4ull << chunk_log)) worth = true;
     if (const char* e = getenv("B381_MSM_CHUNK_LOG")) {          // A/B runs and tests: any size, 31 = off
       chunk_log = (uint32_t)atoi(e);
       worth = levels >= 1 && chunk_log < 31 && (uint64_t)n > (1ull << chunk_log);

@@ -136,7 +136,13 @@ uint32_t msm_sort_piece(const msm_shape& sh) {
     const int v = atoi(e);
     if (v >= 8 && v <= 26) piece = 1u << v;
   }
-  if (sh.nchunks > 1 && (1u << sh.chunk_log) > piece) piece = 1u << sh.chunk_log;   // a piece is a whole number of chunks
+  if (sh.nchunks > 1) {
+    // a piece is a whole number of chunks, and there are at least four pieces when there are four chunks: the last
+    // piece's sort and forward pass are what the copy cannot hide
+    const uint32_t chunk = 1u << sh.chunk_log;
+    while (piece > chunk && (uint64_t)piece * 4 > sh.n) piece >>= 1;
+    if (piece < chunk) piece = chunk;
+  }
   return piece;
 }
 

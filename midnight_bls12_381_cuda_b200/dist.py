@@ -45,6 +45,19 @@ def gather_partials(partial, dist_module=None, group=None):
     return out
 
 
+def gather_partials_into(partial, out, dist_module=None, group=None):
+    """same exchange into ONE preallocated [world, bytes] tensor (no per-rank output tensors, no concatenation before
+    the combine): NCCL all_gather_into_tensor.  Returns `out`."""
+    import torch.distributed as dist
+    d = dist_module or dist
+    world = d.get_world_size(group) if d.is_initialized() else 1
+    if world == 1:
+        out.view(-1)[:partial.numel()].copy_(partial.view(-1))
+        return out
+    d.all_gather_into_tensor(out.view(-1), partial.view(-1), group=group)
+    return out
+
+
 class ShardedMsm:
     """Point-range sharded MSM.  Each rank calls `run` with ITS shard resident on its GPU."""
 
@@ -53,7 +66,7 @@ class ShardedMsm:
         self.curve, self.window = curve, window
         self._lib = L.lib()
 
-    def partial(self, scalars_dev, bases_dev, n_local: int, scalars_mont: bool = True, stream=None):
+    def partial(self, scalars_dev, bases_dev, n_local: int, scalars_mont: bool = True, stream=None, out=None):
         import torch
         cfg = self._lib.b381_default_msm_config()
         cfg.c = self.window
@@ -63,7 +76,8 @@ class ShardedMsm:
         cfg.is_async = True
         if stream is not None:
             cfg.stream = C.c_void_p(stream)
-        out = torch.empty(XYZZ_BYTES[self.curve], dtype=torch.uint8, device="cuda")
+        if out is None:
+            out = torch.empty(XYZZ_BYTES[self.curve], dtype=torch.uint8, device="cuda")
         fn = self._lib.b381_g1_msm_partial if self.curve == "g1" else self._lib.b381_g2_msm_partial
         L.check(fn(L.ptr(scalars_dev), L.ptr(bases_dev), n_local, C.byref(cfg), L.ptr(out)), "msm_partial")
         return out
@@ -71,16 +85,25 @@ class ShardedMsm:
     def combine(self, partials) -> np.ndarray:
         """sum of XYZZ partials -> ICICLE standard-form projective bytes (host)."""
         import torch
-        allp = torch.cat(list(partials)).contiguous()
+        if isinstance(partials, torch.Tensor):               # one [world, bytes] tensor (gather_partials_into)
+            allp, count = partials, partials.numel() * partials.element_size() // XYZZ_BYTES[self.curve]
+        else:
+            allp, count = torch.cat(list(partials)).contiguous(), len(partials)
         k = 18 if self.curve == "g1" else 36
         res = np.zeros(k, dtype=np.uint64)
         fn = self._lib.b381_g1_msm_combine if self.curve == "g1" else self._lib.b381_g2_msm_combine
-        L.check(fn(L.ptr(allp), len(partials), None, False, L.ptr(res)), "msm_combine")
+        L.check(fn(L.ptr(allp), count, None, False, L.ptr(res)), "msm_combine")
         return res
 
     def run(self, scalars_dev, bases_dev, n_local: int, scalars_mont: bool = True, group=None):
-        part = self.partial(scalars_dev, bases_dev, n_local, scalars_mont)
-        return self.combine(gather_partials(part, group=group))
+        import torch
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if getattr(self, "_gathered", None) is None or self._gathered.shape[0] != world:
+            self._gathered = torch.empty((world, XYZZ_BYTES[self.curve]), dtype=torch.uint8, device="cuda")
+            self._part = torch.empty(XYZZ_BYTES[self.curve], dtype=torch.uint8, device="cuda")
+        part = self.partial(scalars_dev, bases_dev, n_local, scalars_mont, out=self._part)
+        return self.combine(gather_partials_into(part, self._gathered, group=group))
 
 
 # ----------------------------------------------------------------------------- four-step NTT

@@ -45,6 +45,9 @@ def _worker(rank, world, port, log_n, ret):
         part = torch.full((192,), rank, dtype=torch.uint8)
         got = D.gather_partials(part)
         assert [int(g[0]) for g in got] == list(range(world))
+        into = torch.empty((world, 192), dtype=torch.uint8)
+        assert D.gather_partials_into(part, into) is into and into[:, 0].tolist() == list(range(world)) \
+            and into[:, 191].tolist() == list(range(world))
         # row exchange: tag every element with its global flat index
         sh = D.fourstep_shape(log_n, world)
         x = np.arange(1 << log_n, dtype=np.int64)
