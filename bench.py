@@ -646,7 +646,10 @@ def main():
                                                              "are_outputs_on_device = false); PCIe-bound: 2 x 0.5 GiB per transform"},
                "roofline": {"bound": "hbm", "achieved": alg_bytes / (ntt_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": alg_bytes / (ntt_ms * 1e-3) / 1e9 / hbm_peak,
-                            "traffic": None, "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
+                            "traffic": 3.659e9 * (n_loc / float(1 << 24)) if passes == 3 else None,
+                            "traffic_source": "dram__bytes_read+write of the three k_ntt launches of one 2^24 transform (1.58 + 1.02 + 1.06 GB), "
+                                              "ncu --set full (profiles/r02h_ntt_key_metrics.txt), scaled by n; achieved/traffic are per transform",
+                            "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                             "kernel": f"k_ntt x{passes}", "note": "compute (IMAD) bound: see imad_frac / fr_mul_floor_frac"},
                "result_check": ntt_check, "gpu_launches": passes}
 
@@ -744,8 +747,8 @@ def main():
                     "name": "k_msm_pair_bwd<fq_t, 32, level 0>", "kernel_ms": ph[9], "share_of_step": ph[9] / ms_step,
                     "achieved": pairs * 1500.0 / (ph[9] * 1e-3) / 1e9, "unit": "GMAD/s", "frac": pairs * 1500.0 / (ph[9] * 1e-3) / imad_peak,
                     "note": "carry-chain IMAD.WIDE.X issues at ~0.57 of the plain IMAD.WIDE peak used as denominator (profiles/r01_imad_variants.txt)",
-                    "traffic": 73.65e9 * (n_loc / float(1 << 24)),
-                    "traffic_source": "dram__bytes_read+write of this kernel at n = 2^24, ncu --set full (profiles/r01c_pair_kernels_key_metrics.txt), scaled by n",
+                    "traffic": 61.23e9 * (n_loc / float(1 << 24)),
+                    "traffic_source": "dram__bytes_read+write of this kernel at n = 2^24 (45.63 + 15.60 GB), ncu --set full (profiles/r02h_msm_key_metrics.txt), scaled by n; algorithmic: 2 x 96 B gathered + 96 B written per pair sum = 38.7 GB",
                     "level0_fwd_ms": ph[8]}
         if ntt:
             # n/2 * log2(n) butterflies, one Fr Montgomery product (2*8^2+8 = 136 multiply-adds) each
