@@ -113,18 +113,14 @@ static void launch_fwd(const uint32_t* in_off, const uint32_t* out_off, uint32_t
 }
 
 template <class F, bool L0>
-static void launch_invert_bwd(const uint32_t* out_off, uint32_t nbuckets, const uint32_t* svals, const level_pts<F> pts,
-                              unsigned g, uint32_t nt, uint32_t* srcg, F* preg, F* tot, F* outx, F* outy, const pair_dst dst,
-                              bool time_it, cudaStream_t st) {
-  constexpr int PB = pair_batch<F>::B, PM = pair_batch<F>::M;
-  const unsigned gi = (unsigned)((((size_t)nt + 3) / 4 + 127) / 128);   // enough for the smallest per-thread batch (4)
+static void launch_bwd(const uint32_t* out_off, uint32_t nbuckets, const uint32_t* svals, const level_pts<F> pts,
+                       unsigned g, uint32_t nt, uint32_t* srcg, F* preg, F* tot, F* outx, F* outy, const pair_dst dst,
+                       bool timed, cudaStream_t st) {
+  constexpr int PB = pair_batch<F>::B;
   // CTAs per SM of the backward kernel: G1 (126 registers at 4, no spill) measured best at 4 on B200
   // (profiles/r01b_msm_levels_sweep.txt); G2's Fq2 state needs the full register file: 254 registers, no spill at 2
   static const int minb = [] { const char* e = getenv("B381_BWD_MINB"); return e ? atoi(e) : 0; }();
   const int mb = minb ? minb : (sizeof(F) > sizeof(fq_t) ? 2 : 4);
-  const bool timed = time_it && L0 && sizeof(F) == sizeof(fq_t) && l0_timing_on();
-  k_msm_invert_totals<F, PB, PM><<<gi, 128, 0, st>>>(out_off, nbuckets, tot);
-  if (timed) cudaEventRecord(g_l0_ev[2], st);
   const uint32_t* dslots = dst.base ? dst.slots : nullptr;
   if (mb == 2) k_msm_pair_bwd<F, PB, L0, 2><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, outx, outy, dslots);
   else if (mb == 3) k_msm_pair_bwd<F, PB, L0, 3><<<g, PR_TPB, 0, st>>>(out_off, nbuckets, svals, pts, nt, srcg, preg, tot, outx, outy, dslots);
@@ -133,6 +129,18 @@ static void launch_invert_bwd(const uint32_t* out_off, uint32_t nbuckets, const 
     cudaEventRecord(g_l0_ev[3], st);
     g_l0_ev_valid = true;
   }
+}
+
+template <class F, bool L0>
+static void launch_invert_bwd(const uint32_t* out_off, uint32_t nbuckets, const uint32_t* svals, const level_pts<F> pts,
+                              unsigned g, uint32_t nt, uint32_t* srcg, F* preg, F* tot, F* outx, F* outy, const pair_dst dst,
+                              bool time_it, cudaStream_t st) {
+  constexpr int PB = pair_batch<F>::B, PM = pair_batch<F>::M;
+  const unsigned gi = (unsigned)((((size_t)nt + 3) / 4 + 127) / 128);   // enough for the smallest per-thread batch (4)
+  const bool timed = time_it && L0 && sizeof(F) == sizeof(fq_t) && l0_timing_on();
+  k_msm_invert_totals<F, PB, PM><<<gi, 128, 0, st>>>(out_off, nbuckets, tot);
+  if (timed) cudaEventRecord(g_l0_ev[2], st);
+  launch_bwd<F, L0>(out_off, nbuckets, svals, pts, g, nt, srcg, preg, tot, outx, outy, dst, timed, st);
 }
 
 // A level pays once there are enough pairs to fill the GPU (each level has ~0.2 ms of fixed latency: three
@@ -181,8 +189,25 @@ void launch_pair_finish_streamed(const uint32_t* in_off, const uint32_t* out_off
                                  uint32_t* dst_slots) {
   const pair_dst dst{dst_base, dst_set_slots, dst_nchunks, dst_slots};
   const uint32_t nt = grid * PR_TPB;
-  k_msm_pair_dst<pair_batch<F>::B><<<grid, PR_TPB, 0, st>>>(in_off, out_off, nbuckets, nt, dst);
-  launch_invert_bwd<F, true>(out_off, nbuckets, svals, pts, grid, nt, srcg, preg, tot, outx, outy, dst, false, st);
+  // The destination walk and the batched inversion are independent (only the backward pass needs both), and the
+  // inversion is latency-bound at 11-20 % occupancy: the walk (0.5 ms at 2^24) runs beside it on a side stream.
+  cudaStream_t side = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+  bool forked = cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking) == cudaSuccess &&
+                cudaEventCreateWithFlags(&fork, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventCreateWithFlags(&join, cudaEventDisableTiming) == cudaSuccess &&
+                cudaEventRecord(fork, st) == cudaSuccess && cudaStreamWaitEvent(side, fork, 0) == cudaSuccess;
+  k_msm_pair_dst<pair_batch<F>::B><<<grid, PR_TPB, 0, forked ? side : st>>>(in_off, out_off, nbuckets, nt, dst);
+  if (forked) forked = cudaEventRecord(join, side) == cudaSuccess;
+  constexpr int PB = pair_batch<F>::B, PM = pair_batch<F>::M;
+  const unsigned gi = (unsigned)((((size_t)nt + 3) / 4 + 127) / 128);
+  k_msm_invert_totals<F, PB, PM><<<gi, 128, 0, st>>>(out_off, nbuckets, tot);
+  if (forked) cudaStreamWaitEvent(st, join, 0);
+  else if (side) cudaStreamSynchronize(side);    // could not record the join: wait on the host (the walk may be on `side`)
+  launch_bwd<F, true>(out_off, nbuckets, svals, pts, grid, nt, srcg, preg, tot, outx, outy, dst, false, st);
+  if (fork) cudaEventDestroy(fork);
+  if (join) cudaEventDestroy(join);
+  if (side) cudaStreamDestroy(side);             // deferred by the runtime until the walk is done
 }
 
 #define B381_INSTANTIATE_PAIR(F)                                                                                          \
