@@ -274,7 +274,8 @@ int b381_ntt_dist_columns_p2p(b381_fr* data_device, int log_n, int log_gpus, int
 int b381_ipc_alloc(size_t bytes, void** ptr, unsigned char handle[64]);
 int b381_ipc_open(const unsigned char handle[64], void** ptr);
 int b381_ipc_close(void* ptr);
-/* Adds `count` XYZZ partials (device) and writes ONE ICICLE standard-form projective result. */
+/* Adds `count` XYZZ partials (device) and writes ONE ICICLE standard-form projective result.  result_on_device = false:
+ * synchronous, the result has landed in host memory on return; true: stream-ordered on `stream`, no host synchronisation. */
 int b381_g1_msm_combine(const void* partials_xyzz_device, int count, void* stream, bool result_on_device,
                         b381_g1_projective* result);
 int b381_g2_msm_combine(const void* partials_xyzz_device, int count, void* stream, bool result_on_device,

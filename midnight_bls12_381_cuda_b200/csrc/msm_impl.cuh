@@ -679,7 +679,9 @@ static int combine_entry(const void* parts, int count, void* stream, bool on_dev
       if (e != cudaSuccess) return map_cuda_error(e);
     }
   }
-  e = cudaStreamSynchronize(st);
+  // a device result is ordered by the caller's stream (no host round trip per step when several MSMs are in flight);
+  // a host result has to have landed when the call returns
+  e = on_device ? cudaGetLastError() : cudaStreamSynchronize(st);
   return map_cuda_error(e);
 }
 

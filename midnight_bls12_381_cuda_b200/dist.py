@@ -82,6 +82,15 @@ class ShardedMsm:
         L.check(fn(L.ptr(scalars_dev), L.ptr(bases_dev), n_local, C.byref(cfg), L.ptr(out)), "msm_partial")
         return out
 
+    def combine_async(self, partials, out_dev, stream=None):
+        """sum of XYZZ partials -> ICICLE standard-form projective words in `out_dev` (device int64[18] / [36]),
+        stream-ordered on `stream`: no host synchronisation, so several sharded MSMs can be in flight."""
+        count = partials.numel() * partials.element_size() // XYZZ_BYTES[self.curve]
+        fn = self._lib.b381_g1_msm_combine if self.curve == "g1" else self._lib.b381_g2_msm_combine
+        L.check(fn(L.ptr(partials), count, C.c_void_p(stream) if stream is not None else None, True, L.ptr(out_dev)),
+                "msm_combine")
+        return out_dev
+
     def combine(self, partials) -> np.ndarray:
         """sum of XYZZ partials -> ICICLE standard-form projective bytes (host)."""
         import torch
