@@ -62,7 +62,6 @@ def parse():
     ap.add_argument("--log-n", type=int, default=24)
     ap.add_argument("--cpu-log-n", type=int, default=0, help="log2 size of the CPU sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--force-value-pipelined", action="store_true", help="time two resident MSMs in flight at any size")
     ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference's own kernels (oracle/_ref) timed beside ours")
     ap.add_argument("--dist-ntt-log", type=int, default=26, help="log2 size of the four-step NTT timed at N > 1")
     return ap.parse_args()
@@ -556,9 +555,12 @@ def main():
     res_cfg.is_async = True
 
     def run_resident_pipelined(k):
+        done = [None, None]
         for i in range(k):
             s = pipe_streams[i & 1]                # step i follows step i - 2 on its stream, so their buffers can be shared
             part, gath, res = pipe_bufs[i & 1]
+            if done[i & 1] is not None:
+                done[i & 1].synchronize()          # at most two steps in flight (what a handle's wait() does for a prover)
             with torch.cuda.stream(s):
                 if world == 1:
                     res_cfg.stream = C.c_void_p(s.cuda_stream)
@@ -567,6 +569,8 @@ def main():
                     msm.partial(sc, bases, n_loc, scalars_mont=True, stream=s.cuda_stream, out=part)
                     D.gather_partials_into(part, gath)
                     msm.combine_async(gath, res, stream=s.cuda_stream)
+                done[i & 1] = torch.cuda.Event()
+                done[i & 1].record(s)
         torch.cuda.synchronize()
         return [b[2].cpu().numpy().view(np.uint64).copy() for b in pipe_bufs[:min(k, 2)]]
 
@@ -612,15 +616,10 @@ def main():
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
-    # Only below 2^23 points per GPU: from there on level 0 lives on ONE L2-resident chunk of the bases at a time
-    # (chunk-major grouping), and two MSMs in flight evict each other's chunk -- measured 120 ms per step instead of
-    # 73.4 at 2^24 on one GPU (profiles/r02h_value_pipelined.txt); at 2^21 per GPU: 12.6 -> 11.1 ms.
-    ms_rpipe, rpipe_res = None, []
-    if n_loc < (1 << 23) or args.force_value_pipelined:
-        run_resident_pipelined(2)         # the pool has to grow to two working sets once; not part of the measurement
-        box2 = {}
-        ms_rpipe, _, _ = timed(lambda: box2.__setitem__("r", run_resident_pipelined(args.steps)), 1)
-        rpipe_res = box2["r"]
+    run_resident_pipelined(2)         # the pool has to grow to two working sets once; not part of the measurement
+    box2 = {}
+    ms_rpipe, _, _ = timed(lambda: box2.__setitem__("r", run_resident_pipelined(args.steps)), 1)
+    rpipe_res = box2["r"]
     ms_pipe, pipe_xy = None, None
     if world == 1:
         run_pipelined(4)          # the pool has to grow to two working sets once; not part of the measurement
@@ -850,13 +849,14 @@ def main():
                 "h2d_bytes_per_step": n_loc * 32, "d2h_bytes_per_step": 144,
                 "note": "GpuMsmContext.msm_with_device_bases_async (own stream per call, host scalars staged by the plugin call), "
                         "two commits in flight"},
-            "value_pipelined": None if ms_rpipe is None else {
+            "value_pipelined": {
                 "value": n / (ms_rpipe / args.steps * 1e-3), "unit": "points/s", "ms_per_step": ms_rpipe / args.steps,
                 "result_check": rpipe_check,
                 "note": "same resident workload, the K steps issued as async C-ABI calls on two alternating streams (two MSMs in "
                         "flight" + ("" if world == 1 else "; all_gather and the stream-ordered combine on the step's stream") +
-                        "), one host synchronisation at the end: the latency-bound tail of one step runs under the affine "
-                        "levels of the next.  Reported beside `value`, which times the steps one after the other"},
+                        "), step i + 2 issued when step i has completed (what a handle's wait() does): the latency-bound tail "
+                        "of one step runs under the affine levels of the next.  Reported beside `value`, which times the steps "
+                        "one after the other"},
             "gpu_launches": (own_launches + 1) * args.steps,
             "gpu_launches_note": "own kernels per MSM step as counted by the library (b381_msm_last_info): histogram, scan "
                                  "(tile / totals / add), scatter, 4 + scan per affine level, task_count/build_tasks, task order "
