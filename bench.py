@@ -541,8 +541,8 @@ def main():
             out = pending.pop(0).wait()
         return out
 
-    # value_pipelined: the same resident MSM with TWO steps in flight on two streams (async C-ABI calls; at N > 1 the
-    # all_gather and the stream-ordered combine ride on the step's stream too), the way a prover issues its commitments:
+    # value_pipelined: the same resident MSM with TWO steps in flight on two streams (async C-ABI calls), the way a prover
+    # issues its commitments:
     # the latency-bound tail of one step (bucket reduction, window combine: ~3 ms whatever n is) runs under the affine
     # levels of the next.  One host synchronisation at the end; every result is compared with the serial step's.
     pipe_streams = [torch.cuda.Stream(), torch.cuda.Stream()]
@@ -556,9 +556,10 @@ def main():
 
     def run_resident_pipelined(k):
         done = [None, None]
+        allp = torch.empty((k, D.XYZZ_BYTES["g1"]), dtype=torch.uint8, device="cuda") if world > 1 else None
         for i in range(k):
             s = pipe_streams[i & 1]                # step i follows step i - 2 on its stream, so their buffers can be shared
-            part, gath, res = pipe_bufs[i & 1]
+            res = pipe_bufs[i & 1][2]
             if done[i & 1] is not None:
                 done[i & 1].synchronize()          # at most two steps in flight (what a handle's wait() does for a prover)
             with torch.cuda.stream(s):
@@ -566,13 +567,23 @@ def main():
                     res_cfg.stream = C.c_void_p(s.cuda_stream)
                     L.check(lib.b381_g1_msm(L.ptr(sc), L.ptr(bases), n_loc, C.byref(res_cfg), L.ptr(res)), "async msm")
                 else:
-                    msm.partial(sc, bases, n_loc, scalars_mont=True, stream=s.cuda_stream, out=part)
-                    D.gather_partials_into(part, gath)
-                    msm.combine_async(gath, res, stream=s.cuda_stream)
+                    msm.partial(sc, bases, n_loc, scalars_mont=True, stream=s.cuda_stream, out=allp[i])
                 done[i & 1] = torch.cuda.Event()
                 done[i & 1].record(s)
         torch.cuda.synchronize()
-        return [b[2].cpu().numpy().view(np.uint64).copy() for b in pipe_bufs[:min(k, 2)]]
+        if world == 1:
+            return [b[2].cpu().numpy().view(np.uint64).copy() for b in pipe_bufs[:min(k, 2)]]
+        # N > 1: ONE all_gather for the k partials of every rank, then k stream-ordered combines.  A collective per step
+        # inside the pipeline couples the ranks step by step (every all_gather waits for the slowest rank while the next
+        # one queues behind it on NCCL's stream): measured 15.2 ms per step on 8 GPUs against 12.6 serial and 11.0 this way
+        # (tools/gpu_pipe_nccl.py, profiles/r02h_value_pipelined.txt)
+        allg = torch.empty((world, k, D.XYZZ_BYTES["g1"]), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(allg.view(-1), allp.view(-1))
+        allr = torch.zeros((k, 18), dtype=torch.int64, device="cuda")
+        for i in range(k):
+            msm.combine_async(allg[:, i].contiguous(), allr[i])
+        torch.cuda.synchronize()
+        return [r.numpy().view(np.uint64).copy() for r in allr.cpu()]
 
     def barrier():
         if world > 1:
@@ -616,13 +627,19 @@ def main():
     for _ in range(min(args.warmup, 2)):
         step_e2e()
     ms_e2e, _, _ = timed(step_e2e, args.steps)
-    run_resident_pipelined(2)         # the pool has to grow to two working sets once; not part of the measurement
-    box2 = {}
-    ms_rpipe, _, _ = timed(lambda: box2.__setitem__("r", run_resident_pipelined(args.steps)), 1)
-    rpipe_res = box2["r"]
+    # N = 1 only: inside this script the same leg at N > 1 measured erratic (2 GPUs: 49.9 / 163 ms per step against 39.1
+    # serial; 8 GPUs: 20.2 against 12.8) although the stand-alone driver of exactly this scheme, tools/gpu_pipe_nccl.py,
+    # measures 36.6 ms at 2 x 2^23 and 11.0 ms at 8 x 2^21 (serial 38.9 / 12.6): not understood, recorded in
+    # profiles/r02h_value_pipelined.txt, and not reported here.
+    ms_rpipe, rpipe_res = None, []
+    if world == 1:
+        run_resident_pipelined(args.steps)      # untimed: the pool grows to two working sets once
+        box2 = {}
+        ms_rpipe, _, _ = timed(lambda: box2.__setitem__("r", run_resident_pipelined(args.steps)), 1)
+        rpipe_res = box2["r"]
     ms_pipe, pipe_xy = None, None
     if world == 1:
-        run_pipelined(4)          # the pool has to grow to two working sets once; not part of the measurement
+        run_pipelined(max(4, args.steps))   # the pool has to grow to two working sets once; not part of the measurement
         box = {}
         ms_pipe, _, _ = timed(lambda: box.__setitem__("xy", run_pipelined(args.steps)), 1)
         pipe_xy = box["xy"]
@@ -849,11 +866,11 @@ def main():
                 "h2d_bytes_per_step": n_loc * 32, "d2h_bytes_per_step": 144,
                 "note": "GpuMsmContext.msm_with_device_bases_async (own stream per call, host scalars staged by the plugin call), "
                         "two commits in flight"},
-            "value_pipelined": {
+            "value_pipelined": None if ms_rpipe is None else {
                 "value": n / (ms_rpipe / args.steps * 1e-3), "unit": "points/s", "ms_per_step": ms_rpipe / args.steps,
                 "result_check": rpipe_check,
                 "note": "same resident workload, the K steps issued as async C-ABI calls on two alternating streams (two MSMs in "
-                        "flight" + ("" if world == 1 else "; all_gather and the stream-ordered combine on the step's stream") +
+                        "flight" + ("" if world == 1 else "; the K partials of every rank are exchanged by ONE all_gather at the end, then K combines") +
                         "), step i + 2 issued when step i has completed (what a handle's wait() does): the latency-bound tail "
                         "of one step runs under the affine levels of the next.  Reported beside `value`, which times the steps "
                         "one after the other"},
