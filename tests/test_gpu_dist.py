@@ -36,6 +36,37 @@ def test_sharded_msm_equals_single(cuda, b381, oracle):
     assert m2.combine(parts).tobytes() == exp2
 
 
+def test_sharded_msm_two_in_flight(cuda, b381, oracle):
+    """Two sharded MSMs in flight the way bench.py / tools/gpu_pipe_nccl.py issue them: async partials on two streams
+    written into ONE [k, world, 192] tensor, then stream-ordered combines with a DEVICE result
+    (b381_g1_msm_combine(result_on_device = true) does not synchronise) -- every result equals the oracle's."""
+    from midnight_bls12_381_cuda_b200 import dist as D
+    n, world, k = 1 << 13, 4, 5
+    bases = oracle.gen_series(1, [5, 0, 0, 0], [9, 0, 0, 0], n)
+    d_b = cuda.from_numpy(bases.view(np.int64)).cuda()
+    scs = [oracle.random_fr(200 + i, n) for i in range(k)]
+    d_ss = [cuda.from_numpy(s.view(np.int64)).cuda() for s in scs]
+    m = D.ShardedMsm("g1")
+    streams = [cuda.cuda.Stream(), cuda.cuda.Stream()]
+    parts = cuda.empty((k, world, 192), dtype=cuda.uint8, device="cuda")
+    out = cuda.zeros((k, 18), dtype=cuda.int64, device="cuda")
+    cuda.cuda.synchronize()
+    for i in range(k):
+        s = streams[i & 1]
+        with cuda.cuda.stream(s):
+            for rank in range(world):
+                b, e = D.shard_range(n, rank, world)
+                m.partial(d_ss[i][b:e], d_b[b:e], e - b, scalars_mont=False, stream=s.cuda_stream, out=parts[i, rank])
+            m.combine_async(parts[i], out[i], stream=s.cuda_stream)
+    cuda.cuda.synchronize()
+    got = out.cpu().numpy().view(np.uint64)
+    for i in range(k):
+        assert got[i].tobytes() == oracle.msm(1, scs[i], bases).tobytes(), i
+    # the gather helper into one preallocated tensor (world = 1 without a process group: a plain copy)
+    into = cuda.zeros((1, 192), dtype=cuda.uint8, device="cuda")
+    assert D.gather_partials_into(parts[0, 0], into) is into and bool((into[0] == parts[0, 0]).all())
+
+
 @pytest.mark.parametrize("log_n,world", [(12, 2), (14, 4), (16, 8), (18, 8)])
 def test_fourstep_ntt_equals_single_gpu(cuda, b381, oracle, log_n, world):
     import midnight_bls12_381_cuda_b200 as M
