@@ -621,6 +621,8 @@ def main():
     msm_info = (C.c_int * 4)()
     lib.b381_msm_last_info(msm_info, 4)          # shape of the G1 MSM just timed (before any other MSM runs)
     clocks = sampler.window(t0, t1) if sampler else None
+    if sampler:
+        sampler.stop()       # polled during the headline region only: the host-latency-sensitive legs below run undisturbed
     # phase events make every call wait for its own completion (PhaseTimer::finish): off for the end-to-end legs, or
     # the "async" handles would serialise
     os.environ["B381_MSM_TIMING"] = "0"
