@@ -94,6 +94,5 @@ for name, fn in (("V0 serial", v0), ("V1 two in flight, per-step all_gather", v1
     if rank == 0:
         print(f"{world} GPUs, 2^{sys.argv[1]} total, K={K}: {name}: {ms.item() / K:.2f} ms per step", flush=True)
 if rank == 0:
-    same = bool((allr[0].cpu() == res[(K - 1) & 1].cpu()).all()) if K % 2 == 1 or True else None
     print("V1 == V2 result:", bool((allr[K - 1].cpu() == res[(K - 1) & 1].cpu()).all()))
 dist.destroy_process_group()
