@@ -478,7 +478,9 @@ static cudaError_t msm_single(Scratch& sc, const fr_t* d_scalars, bool scalars_m
   B381_CUDA_TRY(sc.alloc(&partial, max_tasks));
   B381_CUDA_TRY(sc.alloc(&buckets, (size_t)sh.nbuckets));
   {
-    int variant = 3;   // 166 registers -> 3 CTAs (12 warps) per SM: best of {1,3,4} on B200 (119.4 / 116.0 / 121.8 ms at 2^24)
+    // G1: 166 registers -> 3 CTAs (12 warps) per SM: best of {1,3,4} on B200 (119.4 / 116.0 / 121.8 ms at 2^24).  G2: at that
+    // cap the Fq2 state spills 808 bytes per thread; uncapped (255 registers) 2^20: 2.88 -> 2.44 ms (profiles/r02h_g2_occupancy.txt)
+    int variant = sizeof(F) > sizeof(fq_t) ? 1 : 3;
     const char* e = getenv("B381_ACC_MINB");
     if (e) variant = atoi(e);
     const unsigned g = grid_for(max_tasks, 128);

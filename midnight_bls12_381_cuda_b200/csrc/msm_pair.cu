@@ -17,8 +17,9 @@ struct pair_dst { const uint32_t* base; uint32_t set_slots, nchunks; uint32_t* s
 // nb_search have no offsets yet.  hi_dev == nullptr: one launch over everything.
 struct pair_range { const uint32_t* lo_dev; const uint32_t* hi_dev; uint32_t t0, nb_search, final; };
 
+// CTAs per SM: 4 for G1 (<= 128 registers, no spill); an Fq2 forward pass spilled 408-480 bytes per thread at that cap
 template <class F, int B, bool L0>
-__global__ void __launch_bounds__(PR_TPB, 4) k_msm_pair_fwd(const uint32_t* in_off, const uint32_t* out_off,
+__global__ void __launch_bounds__(PR_TPB, (sizeof(F) > sizeof(fq_t) ? 2 : 4)) k_msm_pair_fwd(const uint32_t* in_off, const uint32_t* out_off,
                                                             uint32_t nbuckets, const uint32_t* svals,
                                                             const level_pts<F> pts, uint32_t nt, uint32_t* srcg,
                                                             F* preg, F* tot, const xrec_t<F>* xs, const pair_dst dst,
